@@ -1,0 +1,160 @@
+/*
+ * rodc.h -- C ABI of librodc.so: the B200 (sm_100a) cascade-inference hot path of
+ * Johnson145/RapidObjectDetectionUsingCascadedCNNs.
+ *
+ * The reference is pure Python; it has no FFI of its own.  Each entry point below
+ * replaces the third-party native call (or Python loop) the reference makes at the
+ * cited file:line, so a maintainer can bind it with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_dev` / device pointer is caller-owned
+ *     (PyTorch allocates); `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success, <0 on error; the message is in rodc_last_error()
+ *     (thread-local).  No exceptions cross the ABI, no CPU fallback exists.
+ *   - the library keeps no global mutable state; the only allocations it owns are
+ *     the per-handle tables of rodc_plan (resampling coefficients, window table)
+ *     and rodc_stage (prepared weights), freed by the matching *_destroy.
+ */
+#ifndef RODC_H
+#define RODC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RODC_VERSION 100
+
+#define RODC_OK            0
+#define RODC_ERR_ARG      -1
+#define RODC_ERR_CUDA     -2
+#define RODC_ERR_NOMEM    -3
+#define RODC_ERR_UNSUP    -4
+
+typedef struct rodc_plan  rodc_plan;    /* pyramid plan + window grid of one frame shape */
+typedef struct rodc_stage rodc_stage;   /* one stage net (weights prepared on the device) */
+
+int         rodc_version(void);
+const char* rodc_last_error(void);
+/* SM count and compute capability of the current device (fails loudly without a GPU). */
+int         rodc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- planner (host only)
+ * Replaces the scale loop and grid of Window.extract_windows
+ * (data/rectangles.py:338-425) and the *_norm properties (:248-262); float64
+ * arithmetic in the reference's exact order.  Level sizes follow
+ * scipy.misc.imresize(arr, ratio) (data/image_info.py:240). */
+int     rodc_plan_create(int img_w, int img_h, int win, double factor, double min_window_length,
+                         rodc_plan** out);
+void    rodc_plan_destroy(rodc_plan* p);
+int     rodc_plan_n_levels(const rodc_plan* p);
+int64_t rodc_plan_n_windows(const rodc_plan* p);
+/* 1 if every window lies inside its level; 0 reproduces the ValueError of Window.raw
+ * (data/rectangles.py:286-289) -> the image is skipped (abstract_inference_app.py:165-183). */
+int     rodc_plan_fits(const rodc_plan* p);
+/* arrays of n_levels entries each (any may be NULL) */
+int     rodc_plan_levels(const rodc_plan* p, double* scale, int32_t* width, int32_t* height,
+                         int32_t* step_x, int32_t* step_y, int32_t* nx, int32_t* ny,
+                         int64_t* first_window, int64_t* byte_offset);
+/* arrays of n_windows entries (norm: [n_windows,4] = xmin,ymin,xmax,ymax in the original) */
+int     rodc_plan_windows(const rodc_plan* p, int32_t* level, int32_t* x, int32_t* y, int32_t* norm);
+int64_t rodc_plan_pyramid_bytes(const rodc_plan* p);   /* packed levels of ONE frame */
+int64_t rodc_plan_scratch_bytes(const rodc_plan* p);   /* horizontal-pass rows of ONE frame */
+
+/* ---------------------------------------------------------------- K1 pyramid
+ * Replaces ImageInfo.raw_scaled -> scipy.misc.imresize -> PIL resize(BILINEAR)
+ * (data/image_info.py:201-250), bit-exact: two passes, 22-bit fixed point, u8 rounding
+ * after each pass, every level from the ORIGINAL frame.
+ *   frames  [n_frames, H, W, 3] u8      pyramid [n_frames, pyramid_bytes] u8
+ *   scratch [n_frames, scratch_bytes] u8 */
+int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, uint8_t* pyramid,
+                 uint8_t* scratch, void* stream);
+
+/* Raw stage-0 windows, order frame -> level -> x -> y (data/rectangles.py:291,409):
+ *   windows [n_frames * n_windows, win, win, 3] u8 */
+int rodc_extract_windows(rodc_plan* p, const uint8_t* pyramid, int n_frames, uint8_t* windows,
+                         void* stream);
+/* Window metadata rows (frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm):
+ *   meta [n_frames * n_windows, 5] i32, frame ids start at frame_id_base */
+int rodc_window_meta(rodc_plan* p, int n_frames, int frame_id_base, int32_t* meta, void* stream);
+
+/* ---------------------------------------------------------------- K4 recrop
+ * Replaces _get_increased_raw_window_for_next_net (inference_cascade_app.py:363-373):
+ * cv2.resize(window.raw_norm, (size,size)), INTER_LINEAR 8U fixed point incl. the 2x
+ * INTER_AREA shortcut, bit-exact.
+ *   frames_base + frame_off[f] -> [frame_hw[f][0], frame_hw[f][1], 3] u8
+ *   meta [n,5] as above        out [n, size, size, 3] u8 */
+int rodc_recrop(const uint8_t* frames_base, const int64_t* frame_off, const int32_t* frame_hw,
+                const int32_t* meta, int64_t n, int size, uint8_t* out, void* stream);
+
+/* ---------------------------------------------------------------- K2 stage net
+ * Replaces session.run of one frozen stage graph (inference_cascade_app.py:196-215,
+ * inference_app.py:156-166; graph = network/net.py:101-240):
+ * conv3x3(3->C)+b+ReLU -> maxpool3x3/1 SAME -> NHWC flatten -> fc1+b+ReLU ->
+ * concat(prev bottleneck) -> fc2+b -> softmax.  Weights in the reference's layouts:
+ * conv HWIO [3,3,3,C], fc1 [in*in*C, fc1_size], fc2 [fc1_size + n_prev, 2]. */
+int  rodc_stage_create(int in_size, int conv_channels, int fc1_size, int n_prev,
+                       const float* conv_w, const float* conv_b,
+                       const float* fc1_w, const float* fc1_b,
+                       const float* fc2_w, const float* fc2_b, rodc_stage** out);
+void rodc_stage_destroy(rodc_stage* s);
+
+#define RODC_SRC_DENSE   0   /* windows already materialised: dense [n,S,S,3] u8            */
+#define RODC_SRC_PYRAMID 1   /* stage 0: read windows in place from the packed pyramid       */
+#define RODC_SRC_RECROP  2   /* stages >=1: crop+resize on the fly from the original frames  */
+typedef struct {
+    int32_t          kind;
+    const uint8_t*   dense;       /* DENSE                                                   */
+    const rodc_plan* plan;        /* PYRAMID: window w -> frame w / n_windows                */
+    const uint8_t*   pyramid;
+    const uint8_t*   frames_base; /* RECROP (see rodc_recrop)                                */
+    const int64_t*   frame_off;
+    const int32_t*   frame_hw;
+    const int32_t*   meta;
+} rodc_window_source;
+
+#define RODC_IMPL_TENSOR 0   /* tcgen05 split-fp16 GEMM (3 MMAs, fp32-grade)                 */
+#define RODC_IMPL_SIMT   1   /* fp32 CUDA-core GEMM (cross-check implementation)             */
+
+int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, int impl);
+/* Forward of windows [first, first+n) of `src`.
+ *   bottleneck [n, ld_bott] f32: columns [0,fc1_size) are written; columns
+ *       [fc1_size, fc1_size+n_prev) must already hold the gathered previous bottleneck
+ *       (written by rodc_compact) when n_prev > 0.
+ *   logits, probs [n,2] f32 (probs = "final_softmax"). */
+int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
+                       float* bottleneck, int ld_bott, float* logits, float* probs,
+                       void* workspace, int64_t workspace_bytes, int impl, void* stream);
+/* Test hook: pooled conv features of the windows, fp32 [n, in*in*C] (NHWC flatten order). */
+int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, int64_t first,
+                            int64_t n, float* features, void* stream);
+
+/* ---------------------------------------------------------------- K3 compaction
+ * Replaces the per-row Python filter (inference_cascade_app.py:219-247): keep window w iff
+ * (double)probs[w,1] > threshold (strict), order preserved; gathers metadata rows, the
+ * bottleneck rows (into columns [col_off, col_off+width) of bott_out) and the confidence
+ * (mode 0 = p, 1 = acc + p, 2 = acc * p).  count_out (device int64) receives the number
+ * kept; keep_idx_out [<=n] i32 the kept positions.  scratch: rodc_compact_scratch_bytes(n). */
+int64_t rodc_compact_scratch_bytes(int64_t n);
+int rodc_compact(const float* probs, int64_t n, double threshold,
+                 const int32_t* meta_in, int32_t* meta_out,
+                 const float* bott_in, int ld_in, int width, float* bott_out, int ld_out, int col_off,
+                 const float* conf_acc_in, float* conf_out, int conf_mode,
+                 int32_t* keep_idx_out, int64_t* count_out, void* scratch, void* stream);
+
+/* ---------------------------------------------------------------- K5 group rectangles
+ * Replaces cv2.groupRectangles(rects, min_neighbors, eps=0.2) per image
+ * (inference_app.py:187-212): union-find on the SimilarRects predicate, per-class
+ * float32 mean + cvRound, size filter, nested filter; classes in order of first member.
+ *   cand [K,5] i32 (frame_id, xmin,ymin,xmax,ymax), grouped by ascending frame id
+ *   out  [K,6] i32 (frame_id, x, y, w, h, weight), frames ascending, class order inside
+ *   out_count: device int64.  scratch: rodc_group_scratch_bytes(K, n_frames). */
+int64_t rodc_group_scratch_bytes(int64_t k, int n_frames);
+int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
+                          int32_t* out, int64_t* out_count, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODC_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of librodc.so (the C ABI declared in include/rodc.h).
+
+There is deliberately NO fallback: if the library is missing it is built in-tree with nvcc
+(``build.py``); if that fails, or a compute entry point is called without a CUDA device, the
+error propagates.  The oracle under ``oracle/`` is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class WindowSource(C.Structure):
+    """``rodc_window_source`` (include/rodc.h)."""
+    _fields_ = [("kind", C.c_int32), ("dense", vp), ("plan", vp), ("pyramid", vp),
+                ("frames_base", vp), ("frame_off", vp), ("frame_hw", vp), ("meta", vp)]
+
+
+SRC_DENSE, SRC_PYRAMID, SRC_RECROP = 0, 1, 2
+IMPL_TENSOR, IMPL_SIMT = 0, 1
+
+# name -> (restype, argtypes); every symbol include/rodc.h declares
+SIGNATURES = {
+    "rodc_version": (C.c_int, []),
+    "rodc_last_error": (C.c_char_p, []),
+    "rodc_device_info": (C.c_int, [c_i32p, c_i32p, c_i32p]),
+    "rodc_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
+    "rodc_plan_destroy": (None, [vp]),
+    "rodc_plan_n_levels": (C.c_int, [vp]),
+    "rodc_plan_n_windows": (C.c_int64, [vp]),
+    "rodc_plan_fits": (C.c_int, [vp]),
+    "rodc_plan_levels": (C.c_int, [vp, c_f64p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i64p, c_i64p]),
+    "rodc_plan_windows": (C.c_int, [vp, c_i32p, c_i32p, c_i32p, c_i32p]),
+    "rodc_plan_pyramid_bytes": (C.c_int64, [vp]),
+    "rodc_plan_scratch_bytes": (C.c_int64, [vp]),
+    "rodc_pyramid": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+    "rodc_extract_windows": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "rodc_window_meta": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "rodc_recrop": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]),
+    "rodc_stage_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "rodc_stage_destroy": (None, [vp]),
+    "rodc_stage_workspace_bytes": (C.c_int64, [vp, C.c_int64, C.c_int]),
+    "rodc_stage_forward": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, C.c_int, vp, vp,
+                                     vp, C.c_int64, C.c_int, vp]),
+    "rodc_stage_features_f32": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, vp]),
+    "rodc_compact_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "rodc_compact": (C.c_int, [vp, C.c_int64, C.c_double, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+                               vp, vp, C.c_int, vp, vp, vp, vp]),
+    "rodc_group_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int]),
+    "rodc_group_rectangles": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp]),
+}
+
+
+class RodcError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (building first if needed) librodc.so and declare every signature."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not os.path.exists(path) or os.environ.get("RODC_REBUILD"):
+            _build.build_library()
+        handle = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().rodc_last_error()
+        raise RodcError("%s failed (%d): %s" % (what or "librodc call", rc, (msg or b"").decode()))

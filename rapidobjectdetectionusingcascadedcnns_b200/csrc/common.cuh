@@ -1,0 +1,61 @@
+// Shared helpers for librodc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <vector>
+#include "../../include/rodc.h"
+
+namespace rodc {
+
+void set_error(const char* fmt, ...);
+
+#define RODC_CHECK_ARG(cond, ...)                                   \
+    do { if (!(cond)) { rodc::set_error(__VA_ARGS__); return RODC_ERR_ARG; } } while (0)
+
+#define RODC_CUDA(call)                                             \
+    do { cudaError_t e__ = (call);                                  \
+         if (e__ != cudaSuccess) {                                  \
+             rodc::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+             return RODC_ERR_CUDA; } } while (0)
+
+#define RODC_LAUNCH_CHECK()  RODC_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct LevelInfo {            // one pyramid level of a plan (host + device copies)
+    double  scale;
+    int32_t w, h;             // level size
+    int32_t step_x, step_y, nx, ny;
+    int64_t first_window;
+    int64_t byte_off;         // offset of the level in a frame's packed pyramid
+    int64_t scratch_off;      // offset of the level's horizontal-pass rows in a frame's scratch
+    int32_t identity;         // scale == 1.0: the level is the frame itself
+    // coefficient tables (offsets into the plan's int32 table buffer)
+    int32_t kx, ky;           // ksize of the horizontal / vertical pass
+    int64_t hx_bounds, hx_coef;   // [w][2] and [w][kx]
+    int64_t vy_bounds, vy_coef;   // [h][2] and [h][ky]
+};
+
+}  // namespace rodc
+
+struct rodc_plan {
+    int img_w, img_h, win;
+    double factor, min_window_length;
+    std::vector<rodc::LevelInfo> levels;
+    std::vector<int32_t> win_level, win_x, win_y, norm;       // norm: [N*4]
+    std::vector<int32_t> tables;                               // bounds + coefficients of all levels
+    int64_t pyramid_bytes = 0, scratch_bytes = 0;
+    int fits = 1;
+    // device copies (lazily uploaded on first GPU use; device of first use)
+    int device = -1;
+    rodc::LevelInfo* d_levels = nullptr;
+    int32_t* d_tables = nullptr;
+    int32_t* d_win = nullptr;          // [N, 8]: level, x, y, level_w, norm[4] -- see plan.cu
+    int32_t* d_row_start = nullptr;    // [n_levels+1] prefix of level heights (vertical-pass grid)
+    int total_rows = 0;
+    int ensure_device();
+    ~rodc_plan();
+};

@@ -1,0 +1,251 @@
+// K2b: fc1 (flatten -> 512, + bias + ReLU; network/net.py:233-236) on the 5th-gen tensor cores.
+//
+//   bottleneck[m, 512] = relu( A[m, K] * W[K, 512] + b )       K = S*S*32 = 4608 / 18432 / 73728
+//
+// Precision.  Raw 0..255 inputs and Xavier weights give logits of O(10^2); the survivor set must
+// match an fp64 evaluation except within 1e-4 of the threshold, which a bf16 or tf32 GEMM cannot
+// deliver (tf32 -> 2e-2 mean margin error, bf16 -> 2e-1).  Both operands are
+// therefore split into two fp16 terms (x * 2^e = hi + lo, 22 significant bits) and the product is
+// formed with THREE kind::f16 MMAs into the same fp32 TMEM accumulator:
+//       A_hi*B_lo + A_lo*B_hi + A_hi*B_hi           (the dropped lo*lo term is < 2^-22 relative)
+// i.e. fp32-grade products at 1/3 of the fp16 tensor peak instead of a CUDA-core SGEMM.
+//
+// Structure (one CTA per 128 x 256 output tile, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, 4 tiles per stage
+//                              (A_hi, A_lo: 128 x 64 fp16; B_hi, B_lo: 256 x 64 fp16 = 96 KB/stage)
+//   warp 1      TMEM alloc + MMA issuer (one lane): 4 k-steps x 3 tcgen05.mma (M128 N256 K16) per
+//               stage, tcgen05.commit -> empty barrier (smem slot free) / tmem_full barrier
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (one TMEM lane quarter each) -> scale 2^-(ea+ew),
+//               + bias, ReLU -> fp32 rows of the concat buffer
+#include "stage.cuh"
+#include <cuda.h>
+
+namespace rodc {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int A_TILE = BM * BK * 2;                 // 16 KB
+constexpr int B_TILE = BN * BK * 2;                 // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused: one swizzle atom along K),
+//   [32,46) SBO >> 4 = 1024 B (8 rows x 128 B), [46,48) version = 1, [61,64) layout = 2 (SW128).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, M128 x N256.
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(THREADS, 1)
+fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, float out_scale) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] tmem_full; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x & 1, m_tile = blockIdx.x >> 1;
+    const int m0 = m_tile * BM, n0 = n_tile * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[STAGES + s]), 1); }
+        mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bars[s]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
+                tma_load_2d(base + A_TILE, &map_a_lo, full, kb * BK, m0);
+                tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
+                tma_load_2d(base + 2 * A_TILE + B_TILE, &map_b_lo, full, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                #pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 2;             // bytes along K inside the 128 B swizzle row
+                    const uint64_t a_hi = smem_desc_sw128(base + koff);
+                    const uint64_t a_lo = smem_desc_sw128(base + A_TILE + koff);
+                    const uint64_t b_hi = smem_desc_sw128(base + 2 * A_TILE + koff);
+                    const uint64_t b_lo = smem_desc_sw128(base + 2 * A_TILE + B_TILE + koff);
+                    umma_f16(tmem_base, a_hi, b_lo, IDESC, (kb | k) != 0);
+                    umma_f16(tmem_base, a_lo, b_hi, IDESC, 1u);
+                    umma_f16(tmem_base, a_hi, b_hi, IDESC, 1u);
+                }
+                umma_commit(smem_u32(&bars[STAGES + s]));            // smem slot free once these MMAs retire
+            }
+            umma_commit(smem_u32(&bars[2 * STAGES]));                // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+        const int q = warp & 3;
+        mbar_wait(smem_u32(&bars[2 * STAGES]), 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+        float* orow = out + (int64_t)row * ld_out + n0;
+        #pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (row < m) {
+                #pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = fmaxf(fmaf(v[j + 0], out_scale, __ldg(bias + n0 + c + j + 0)), 0.f);
+                    o.y = fmaxf(fmaf(v[j + 1], out_scale, __ldg(bias + n0 + c + j + 1)), 0.f);
+                    o.z = fmaxf(fmaf(v[j + 2], out_scale, __ldg(bias + n0 + c + j + 2)), 0.f);
+                    o.w = fmaxf(fmaf(v[j + 3], out_scale, __ldg(bias + n0 + c + j + 3)), 0.f);
+                    *reinterpret_cast<float4*>(orow + c + j) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, K] fp16 row-major, box = box_rows x 64 elements, 128 B swizzle, OOB rows read as zero
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RODC_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RODC_ERR_CUDA; }
+    return RODC_OK;
+}
+
+}  // namespace tc
+
+int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
+                      float* bott, int ld_bott, cudaStream_t st) {
+    using namespace tc;
+    if (m <= 0) return RODC_OK;
+    RODC_CHECK_ARG(s->fc1_size == 2 * BN, "tensor fc1 is built for fc1_size == 512 (got %d)", s->fc1_size);
+    RODC_CHECK_ARG(s->K % BK == 0, "K must be a multiple of %d", BK);
+    RODC_CHECK_ARG(m < (1ll << 30) && ld_bott % 4 == 0, "bad m / ld_bott");
+    RODC_CHECK_ARG((reinterpret_cast<uintptr_t>(bott) & 15) == 0, "bottleneck buffer must be 16-byte aligned");
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
+        (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN))) return rc;
+    RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const unsigned tiles = (unsigned)((m + BM - 1) / BM) * 2u;
+    const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
+    fc1_tc_kernel<<<tiles, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
+                                                      (int)(s->K / BK), out_scale);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+}  // namespace rodc

@@ -1,0 +1,164 @@
+// K2 host side: stage handle (weights prepared on the device) and the stage forward
+// (features -> fc1 -> fc2/softmax), chunked over the caller's workspace.
+// Replaces session.run of one frozen stage graph (app/inference_cascade_app.py:196-215).
+#include "stage.cuh"
+#include <math.h>
+#include <string.h>
+#include <new>
+
+rodc_stage::~rodc_stage() {
+    float* f[] = {conv_w, conv_b, fc1_w, fc1_b, fc2_w, fc2_b};
+    for (float* p : f) if (p) cudaFree(p);
+    if (fc1_hi) cudaFree(fc1_hi);
+    if (fc1_lo) cudaFree(fc1_lo);
+}
+
+namespace rodc {
+
+// W[K, N] fp32 (N contiguous) -> hi/lo fp16 planes [N, K] (K contiguous), W * 2^w_exp = hi + lo.
+// 32x32 smem transpose so both the read and the writes are coalesced.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ W, int64_t K, int N, float scale,
+                                                              __half* __restrict__ hi, __half* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int64_t k0 = (int64_t)blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t k = k0 + r;
+        tile[r][tx] = (k < K && n0 + tx < N) ? W[k * N + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r; const int64_t k = k0 + tx;
+        if (n < N && k < K) {
+            const float v = tile[tx][r] * scale;
+            const __half h = __float2half_rn(v);
+            hi[(int64_t)n * K + k] = h;
+            lo[(int64_t)n * K + k] = __float2half_rn(v - __half2float(h));
+        }
+    }
+}
+
+int prepare_fc1_split(rodc_stage* s, cudaStream_t st) {
+    dim3 grid((unsigned)((s->K + 31) / 32), (unsigned)((s->fc1_size + 31) / 32));
+    split_transpose_kernel<<<grid, 256, 0, st>>>(s->fc1_w, s->K, s->fc1_size, ldexpf(1.f, s->w_exp), s->fc1_hi, s->fc1_lo);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+static int upload(float** dst, const float* src, size_t n) {
+    RODC_CUDA(cudaMalloc(dst, (n ? n : 1) * sizeof(float)));
+    if (n) RODC_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return RODC_OK;
+}
+
+// largest e with bound * 2^e <= limit
+static int pow2_headroom(double bound, double limit) {
+    if (!(bound > 0.0)) return 0;
+    int e = (int)floor(log2(limit / bound));
+    if (e > 30) e = 30;
+    if (e < -30) e = -30;
+    return e;
+}
+
+}  // namespace rodc
+
+using namespace rodc;
+
+extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, int n_prev,
+                                 const float* conv_w, const float* conv_b,
+                                 const float* fc1_w, const float* fc1_b,
+                                 const float* fc2_w, const float* fc2_b, rodc_stage** out) {
+    RODC_CHECK_ARG(out && conv_w && conv_b && fc1_w && fc1_b && fc2_w && fc2_b, "rodc_stage_create: NULL argument");
+    RODC_CHECK_ARG(in_size >= 4 && (in_size % 4) == 0 && in_size <= 256, "rodc_stage_create: unsupported input size %d", in_size);
+    RODC_CHECK_ARG(conv_channels == 32, "rodc_stage_create: only 32 conv channels are built (got %d)", conv_channels);
+    RODC_CHECK_ARG(fc1_size > 0 && fc1_size % 256 == 0, "rodc_stage_create: fc1_size must be a multiple of 256 (got %d)", fc1_size);
+    RODC_CHECK_ARG(n_prev >= 0 && n_prev % 4 == 0, "rodc_stage_create: bad previous-bottleneck width %d", n_prev);
+    rodc_stage* s = new (std::nothrow) rodc_stage();
+    if (!s) { set_error("out of host memory"); return RODC_ERR_NOMEM; }
+    s->in_size = in_size; s->channels = conv_channels; s->fc1_size = fc1_size; s->n_prev = n_prev;
+    s->K = (int64_t)in_size * in_size * conv_channels;
+    int rc = cudaGetDevice(&s->device) == cudaSuccess ? RODC_OK : RODC_ERR_CUDA;
+    if (rc) { set_error("no CUDA device"); delete s; return rc; }
+    const size_t nconv = (size_t)27 * conv_channels, nfc1 = (size_t)s->K * fc1_size, nfc2 = (size_t)(fc1_size + n_prev) * 2;
+    if ((rc = upload(&s->conv_w, conv_w, nconv)) || (rc = upload(&s->conv_b, conv_b, conv_channels)) ||
+        (rc = upload(&s->fc1_w, fc1_w, nfc1)) || (rc = upload(&s->fc1_b, fc1_b, fc1_size)) ||
+        (rc = upload(&s->fc2_w, fc2_w, nfc2)) || (rc = upload(&s->fc2_b, fc2_b, 2))) { delete s; return rc; }
+    // scaling exponents for the fp16 split: bound the largest possible feature / weight
+    double fbound = 0.0;
+    for (int c = 0; c < conv_channels; ++c) {
+        double l1 = 0.0;
+        for (int t = 0; t < 27; ++t) l1 += fabs((double)conv_w[t * conv_channels + c]);
+        double b = 255.0 * l1 + fabs((double)conv_b[c]);
+        if (b > fbound) fbound = b;
+    }
+    double wmax = 0.0;
+    for (size_t i = 0; i < nfc1; ++i) { double a = fabs((double)fc1_w[i]); if (a > wmax) wmax = a; }
+    s->a_exp = pow2_headroom(fbound, 32768.0);
+    s->w_exp = pow2_headroom(wmax, 16384.0);
+    cudaError_t e1 = cudaMalloc(&s->fc1_hi, nfc1 * sizeof(__half));
+    cudaError_t e2 = cudaMalloc(&s->fc1_lo, nfc1 * sizeof(__half));
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("cudaMalloc of the split fc1 weights failed"); delete s; return RODC_ERR_NOMEM; }
+    if ((rc = prepare_fc1_split(s, 0))) { delete s; return rc; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("weight preparation failed: %s", cudaGetErrorString(cudaGetLastError())); delete s; return RODC_ERR_CUDA; }
+    *out = s;
+    return RODC_OK;
+}
+
+extern "C" void rodc_stage_destroy(rodc_stage* s) { delete s; }
+
+// workspace = feature chunk: fp32 [m,K] (SIMT) or two fp16 planes [m,K] (tensor): 4*K bytes per window
+static int64_t chunk_windows(const rodc_stage* s, int64_t workspace_bytes) {
+    int64_t m = workspace_bytes / (s->K * 4);
+    if (m >= 128) m = m / 128 * 128;
+    return m;
+}
+
+extern "C" int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, int impl) {
+    (void)impl;
+    if (!s || n < 0) return -1;
+    // enough for two full waves of 128-window tiles on 148 SMs, capped at the problem size
+    int64_t m = (n + 127) / 128 * 128;
+    const int64_t cap = 148 * 128 * (s->K > 40000 ? 1 : (s->K > 10000 ? 2 : 8));
+    if (m > cap) m = cap;
+    if (m < 128) m = 128;
+    return m * s->K * 4;
+}
+
+extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
+                                  float* bottleneck, int ld_bott, float* logits, float* probs,
+                                  void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+    RODC_CHECK_ARG(s && src && bottleneck && probs && workspace, "rodc_stage_forward: NULL argument");
+    RODC_CHECK_ARG(ld_bott >= s->fc1_size + s->n_prev, "rodc_stage_forward: ld_bott %d < %d", ld_bott, s->fc1_size + s->n_prev);
+    RODC_CHECK_ARG(impl == RODC_IMPL_TENSOR || impl == RODC_IMPL_SIMT, "rodc_stage_forward: unknown impl %d", impl);
+    if (n <= 0) return RODC_OK;
+    SrcDev sd;
+    int rc = resolve_source(src, s->in_size, &sd); if (rc) return rc;
+    const int64_t chunk = chunk_windows(s, workspace_bytes);
+    RODC_CHECK_ARG(chunk >= 1, "rodc_stage_forward: workspace too small (%lld bytes, need >= %lld)",
+                   (long long)workspace_bytes, (long long)(s->K * 4));
+    cudaStream_t st = as_stream(stream);
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t m = (n - c0) < chunk ? (n - c0) : chunk;
+        float* bott = bottleneck + c0 * ld_bott;
+        if (impl == RODC_IMPL_SIMT) {
+            float* feat = reinterpret_cast<float*>(workspace);
+            if ((rc = launch_features(s, sd, first + c0, m, feat, nullptr, nullptr, st))) return rc;
+            if ((rc = launch_fc1_simt(s, feat, m, bott, ld_bott, st))) return rc;
+        } else {
+            __half* hi = reinterpret_cast<__half*>(workspace);
+            __half* lo = hi + m * s->K;
+            if ((rc = launch_features(s, sd, first + c0, m, nullptr, hi, lo, st))) return rc;
+            if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
+        }
+    }
+    return launch_fc2_softmax(s, bottleneck, ld_bott, n, logits, probs, st);
+}
+
+extern "C" int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, int64_t first,
+                                       int64_t n, float* features, void* stream) {
+    RODC_CHECK_ARG(s && src && features, "rodc_stage_features_f32: NULL argument");
+    SrcDev sd;
+    int rc = resolve_source(src, s->in_size, &sd); if (rc) return rc;
+    return launch_features(s, sd, first, n, features, nullptr, nullptr, as_stream(stream));
+}

@@ -1,0 +1,50 @@
+// Stage-net handle shared by the K2 kernels.
+#pragma once
+#include "common.cuh"
+
+struct rodc_stage {
+    int in_size = 0;        // S: input window side
+    int channels = 0;       // conv output channels (32)
+    int fc1_size = 0;       // 512
+    int n_prev = 0;         // width of the previous bottleneck (512 * stage index)
+    int64_t K = 0;          // S*S*channels
+    int device = -1;
+    // fp32 weights (reference layouts)
+    float* conv_w = nullptr;    // [3,3,3,C] HWIO
+    float* conv_b = nullptr;    // [C]
+    float* fc1_w = nullptr;     // [K, fc1]      (SIMT path)
+    float* fc1_b = nullptr;     // [fc1]
+    float* fc2_w = nullptr;     // [fc1 + n_prev, 2]
+    float* fc2_b = nullptr;     // [2]
+    // split-fp16 fc1 weights for the tensor path: W * 2^w_exp = hi + lo, stored [fc1, K] (K-major)
+    __half* fc1_hi = nullptr;
+    __half* fc1_lo = nullptr;
+    int a_exp = 0;              // features are scaled by 2^a_exp before the fp16 split
+    int w_exp = 0;              // weights  are scaled by 2^w_exp before the fp16 split
+    ~rodc_stage();
+};
+
+namespace rodc {
+
+// Resolved window source passed by value to the feature kernel.
+struct SrcDev {
+    int kind;
+    const uint8_t* dense;
+    const uint8_t* pyramid; int64_t pyramid_bytes; const LevelInfo* levels; const int32_t* win; int64_t n_windows;
+    const uint8_t* frames_base; const int64_t* frame_off; const int32_t* frame_hw; const int32_t* meta;
+};
+
+int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out);
+
+// features.cu
+int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
+                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st);
+// fc.cu
+int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bott, int ld_bott, cudaStream_t st);
+int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st);
+// fc1_tc.cu
+int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
+                      float* bott, int ld_bott, cudaStream_t st);
+int prepare_fc1_split(rodc_stage* s, cudaStream_t st);
+
+}  // namespace rodc

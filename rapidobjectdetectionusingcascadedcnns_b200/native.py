@@ -1,0 +1,288 @@
+"""Torch-tensor level wrappers over the C ABI (PyTorch = device memory + streams only).
+
+Every function takes CUDA tensors, passes raw pointers + the current stream to librodc and
+returns CUDA tensors; nothing here computes on the host and nothing falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMPL_SIMT, IMPL_TENSOR, SRC_DENSE, SRC_PYRAMID, SRC_RECROP, WindowSource, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.RodcError("librodc operates on CUDA tensors only (no CPU fallback)")
+
+
+def device_info() -> Tuple[int, int, int]:
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    check(_lib.lib().rodc_device_info(C.byref(a), C.byref(b), C.byref(c)), "rodc_device_info")
+    return a.value, b.value, c.value
+
+
+# --------------------------------------------------------------------------------- plan
+class Plan:
+    """Pyramid plan + window grid of one frame shape (host planner of librodc).
+
+    Mirrors the scale loop / grid of ``Window.extract_windows`` (data/rectangles.py:338-425)."""
+
+    def __init__(self, img_w: int, img_h: int, win: int, factor: float = 1.1, min_window_length: float = 0.075):
+        L = _lib.lib()
+        h = C.c_void_p()
+        check(L.rodc_plan_create(int(img_w), int(img_h), int(win), float(factor), float(min_window_length), C.byref(h)),
+              "rodc_plan_create")
+        self._h = h
+        self.img_w, self.img_h, self.win = int(img_w), int(img_h), int(win)
+        self.factor, self.min_window_length = float(factor), float(min_window_length)
+        self.n_levels = L.rodc_plan_n_levels(h)
+        self.n_windows = int(L.rodc_plan_n_windows(h))
+        self.fits = bool(L.rodc_plan_fits(h))
+        self.pyramid_bytes = int(L.rodc_plan_pyramid_bytes(h))
+        self.scratch_bytes = int(L.rodc_plan_scratch_bytes(h))
+        nl, nw = max(self.n_levels, 1), max(self.n_windows, 1)
+        self.scale = np.zeros(nl, np.float64)
+        self.level_w = np.zeros(nl, np.int32); self.level_h = np.zeros(nl, np.int32)
+        self.step_x = np.zeros(nl, np.int32); self.step_y = np.zeros(nl, np.int32)
+        self.nx = np.zeros(nl, np.int32); self.ny = np.zeros(nl, np.int32)
+        self.first_window = np.zeros(nl, np.int64); self.byte_offset = np.zeros(nl, np.int64)
+        p32 = lambda a: a.ctypes.data_as(_lib.c_i32p)
+        check(L.rodc_plan_levels(h, self.scale.ctypes.data_as(_lib.c_f64p), p32(self.level_w), p32(self.level_h),
+                                 p32(self.step_x), p32(self.step_y), p32(self.nx), p32(self.ny),
+                                 self.first_window.ctypes.data_as(_lib.c_i64p),
+                                 self.byte_offset.ctypes.data_as(_lib.c_i64p)), "rodc_plan_levels")
+        self.win_level = np.zeros(nw, np.int32); self.win_x = np.zeros(nw, np.int32); self.win_y = np.zeros(nw, np.int32)
+        self.norm = np.zeros((nw, 4), np.int32)
+        check(L.rodc_plan_windows(h, p32(self.win_level), p32(self.win_x), p32(self.win_y), p32(self.norm)),
+              "rodc_plan_windows")
+        for name in ("scale", "level_w", "level_h", "step_x", "step_y", "nx", "ny", "first_window", "byte_offset"):
+            setattr(self, name, getattr(self, name)[:self.n_levels])
+        self.win_level, self.win_x, self.win_y = (a[:self.n_windows] for a in (self.win_level, self.win_x, self.win_y))
+        self.norm = self.norm[:self.n_windows]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().rodc_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def pyramid(plan: Plan, frames: torch.Tensor, out: Optional[torch.Tensor] = None,
+            scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1.  frames ``[n,H,W,3]`` u8 CUDA -> packed pyramid ``[n, plan.pyramid_bytes]`` u8."""
+    _require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous()
+    n = frames.shape[0]
+    assert tuple(frames.shape[1:]) == (plan.img_h, plan.img_w, 3), (frames.shape, plan.img_h, plan.img_w)
+    if out is None:
+        out = torch.empty((n, plan.pyramid_bytes), dtype=torch.uint8, device=frames.device)
+    if scratch is None:
+        scratch = torch.empty((n, plan.scratch_bytes), dtype=torch.uint8, device=frames.device)
+    check(_lib.lib().rodc_pyramid(plan.handle, _ptr(frames), n, _ptr(out), _ptr(scratch), _stream()), "rodc_pyramid")
+    return out
+
+
+def pyramid_level(plan: Plan, pyr: torch.Tensor, frame: int, level: int) -> torch.Tensor:
+    """View of one level ``[h,w,3]`` inside a packed pyramid (for tests)."""
+    off = int(plan.byte_offset[level]); h = int(plan.level_h[level]); w = int(plan.level_w[level])
+    return pyr[frame, off:off + h * w * 3].view(h, w, 3)
+
+
+def extract_windows(plan: Plan, pyr: torch.Tensor) -> torch.Tensor:
+    """Raw stage-0 windows ``[n*N, win, win, 3]`` u8 (``Window.raw`` for every grid position)."""
+    _require_cuda(pyr)
+    n = pyr.shape[0]
+    out = torch.empty((n * plan.n_windows, plan.win, plan.win, 3), dtype=torch.uint8, device=pyr.device)
+    check(_lib.lib().rodc_extract_windows(plan.handle, _ptr(pyr), n, _ptr(out), _stream()), "rodc_extract_windows")
+    return out
+
+
+def window_meta(plan: Plan, n_frames: int, frame_id_base: int, device) -> torch.Tensor:
+    out = torch.empty((n_frames * plan.n_windows, 5), dtype=torch.int32, device=device)
+    with torch.cuda.device(out.device):
+        check(_lib.lib().rodc_window_meta(plan.handle, n_frames, frame_id_base, _ptr(out), _stream()), "rodc_window_meta")
+    return out
+
+
+class FrameTable:
+    """Device table of the original frames for the RECROP source: one flat u8 buffer plus
+    per-frame byte offsets and (H, W)."""
+
+    def __init__(self, base: torch.Tensor, offsets: Sequence[int], hw: Sequence[Tuple[int, int]]):
+        _require_cuda(base)
+        self.base = base
+        self.off = torch.tensor(list(offsets), dtype=torch.int64, device=base.device)
+        self.hw = torch.tensor([list(x) for x in hw], dtype=torch.int32, device=base.device).reshape(-1, 2)
+        self.n = len(offsets)
+
+    @staticmethod
+    def from_batch(frames: torch.Tensor) -> "FrameTable":
+        n, h, w, _ = frames.shape
+        return FrameTable(frames, [i * h * w * 3 for i in range(n)], [(h, w)] * n)
+
+    @staticmethod
+    def from_list(frames: List[torch.Tensor]) -> "FrameTable":
+        flat = torch.cat([f.reshape(-1) for f in frames])
+        offs, o = [], 0
+        for f in frames:
+            offs.append(o); o += f.numel()
+        return FrameTable(flat, offs, [(f.shape[0], f.shape[1]) for f in frames])
+
+
+def recrop(table: FrameTable, meta: torch.Tensor, size: int) -> torch.Tensor:
+    """K4 standalone: ``cv2.resize(frame[y0:y1, x0:x1], (size,size))`` per meta row -> ``[n,size,size,3]`` u8."""
+    _require_cuda(meta)
+    n = meta.shape[0]
+    out = torch.empty((n, size, size, 3), dtype=torch.uint8, device=meta.device)
+    check(_lib.lib().rodc_recrop(_ptr(table.base), _ptr(table.off), _ptr(table.hw), _ptr(meta), n, size, _ptr(out),
+                                 _stream()), "rodc_recrop")
+    return out
+
+
+# --------------------------------------------------------------------------------- stage
+class Stage:
+    """One stage net on the device (weights in the reference's layouts, see stage_model.py)."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], device=None):
+        if not torch.cuda.is_available():
+            raise _lib.RodcError("a CUDA device is required (no CPU fallback)")
+        cw = np.ascontiguousarray(weights["conv0_W"], np.float32)
+        assert cw.shape[:3] == (3, 3, 3), "default architecture: one 3x3 conv over RGB"
+        self.channels = int(cw.shape[3])
+        f1 = np.ascontiguousarray(weights["fc1_W"], np.float32)
+        self.K, self.fc1_size = int(f1.shape[0]), int(f1.shape[1])
+        self.in_size = int(round((self.K // self.channels) ** 0.5))
+        assert self.in_size * self.in_size * self.channels == self.K
+        f2 = np.ascontiguousarray(weights["fc2_W"], np.float32)
+        self.n_prev = int(f2.shape[0]) - self.fc1_size
+        self.width = self.fc1_size + self.n_prev
+        arrs = [cw, np.ascontiguousarray(weights["conv0_b"], np.float32), f1,
+                np.ascontiguousarray(weights["fc1_b"], np.float32), f2,
+                np.ascontiguousarray(weights["fc2_b"], np.float32)]
+        h = C.c_void_p()
+        ctx = torch.cuda.device(device) if device is not None else torch.cuda.device(torch.cuda.current_device())
+        with ctx:
+            torch.cuda.init()
+            check(_lib.lib().rodc_stage_create(self.in_size, self.channels, self.fc1_size, self.n_prev,
+                                               *[C.c_void_p(a.ctypes.data) for a in arrs], C.byref(h)),
+                  "rodc_stage_create")
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace_bytes(self, n: int, impl: int = IMPL_TENSOR) -> int:
+        return int(_lib.lib().rodc_stage_workspace_bytes(self._h, int(n), impl))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().rodc_stage_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def make_source(*, dense: Optional[torch.Tensor] = None, plan: Optional[Plan] = None,
+                pyr: Optional[torch.Tensor] = None, table: Optional[FrameTable] = None,
+                meta: Optional[torch.Tensor] = None) -> WindowSource:
+    s = WindowSource()
+    if dense is not None:
+        _require_cuda(dense)
+        assert dense.dtype == torch.uint8 and dense.is_contiguous()
+        s.kind = SRC_DENSE; s.dense = dense.data_ptr()
+    elif plan is not None:
+        _require_cuda(pyr)
+        s.kind = SRC_PYRAMID; s.plan = plan.handle.value; s.pyramid = pyr.data_ptr()
+    else:
+        _require_cuda(meta)
+        assert meta.dtype == torch.int32 and meta.is_contiguous()
+        s.kind = SRC_RECROP; s.frames_base = table.base.data_ptr(); s.frame_off = table.off.data_ptr()
+        s.frame_hw = table.hw.data_ptr(); s.meta = meta.data_ptr()
+    return s
+
+
+def stage_forward(stage: Stage, src: WindowSource, first: int, n: int, bottleneck: torch.Tensor,
+                  workspace: torch.Tensor, impl: int = IMPL_TENSOR,
+                  logits: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None):
+    """K2.  Writes ``bottleneck[:, :fc1]``; returns ``(logits [n,2], probs [n,2])``."""
+    _require_cuda(bottleneck, workspace)
+    dev = bottleneck.device
+    assert bottleneck.dtype == torch.float32 and bottleneck.stride(1) == 1 and bottleneck.shape[0] >= n
+    if logits is None:
+        logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    if probs is None:
+        probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    check(_lib.lib().rodc_stage_forward(stage.handle, C.byref(src), int(first), int(n), _ptr(bottleneck),
+                                        int(bottleneck.stride(0)), _ptr(logits), _ptr(probs), _ptr(workspace),
+                                        int(workspace.numel() * workspace.element_size()), int(impl), _stream()),
+          "rodc_stage_forward")
+    return logits, probs
+
+
+def stage_features(stage: Stage, src: WindowSource, first: int, n: int, device) -> torch.Tensor:
+    out = torch.empty((n, stage.K), dtype=torch.float32, device=device)
+    check(_lib.lib().rodc_stage_features_f32(stage.handle, C.byref(src), int(first), int(n), _ptr(out), _stream()),
+          "rodc_stage_features_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------- compaction
+CONF_LAST, CONF_AVG, CONF_MULT = 0, 1, 2
+
+
+def compact(probs: torch.Tensor, n: int, threshold: float, *, meta_in=None, meta_out=None,
+            bott_in=None, width: int = 0, bott_out=None, col_off: int = 0,
+            conf_acc=None, conf_out=None, conf_mode: int = CONF_LAST,
+            keep_idx: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None):
+    """K3.  Returns ``(keep_idx i32 [n], count i64 [1])`` -- both on the device (no sync)."""
+    _require_cuda(probs)
+    dev = probs.device
+    if keep_idx is None:
+        keep_idx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    if count is None:
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    scratch = torch.empty((int(L.rodc_compact_scratch_bytes(int(n))),), dtype=torch.uint8, device=dev)
+    check(L.rodc_compact(_ptr(probs), int(n), float(threshold), _ptr(meta_in), _ptr(meta_out),
+                         _ptr(bott_in), int(bott_in.stride(0)) if bott_in is not None else 0, int(width),
+                         _ptr(bott_out), int(bott_out.stride(0)) if bott_out is not None else 0, int(col_off),
+                         _ptr(conf_acc), _ptr(conf_out), int(conf_mode), _ptr(keep_idx), _ptr(count), _ptr(scratch),
+                         _stream()), "rodc_compact")
+    return keep_idx, count
+
+
+# --------------------------------------------------------------------------------- group rectangles
+def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: int = 1, eps: float = 0.2):
+    """K5.  cand ``[K,5]`` i32 (frame, xmin,ymin,xmax,ymax) grouped by frame ->
+    ``(out [K,6] i32 (frame,x,y,w,h,weight), count i64 [1])`` on the device."""
+    _require_cuda(cand)
+    dev = cand.device
+    out = torch.empty((max(k, 1), 6), dtype=torch.int32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    scratch = torch.empty((int(L.rodc_group_scratch_bytes(int(k), int(n_frames))),), dtype=torch.uint8, device=dev)
+    check(L.rodc_group_rectangles(_ptr(cand), int(k), int(n_frames), int(min_neighbors), float(eps), _ptr(out),
+                                  _ptr(count), _ptr(scratch), _stream()), "rodc_group_rectangles")
+    return out, count
