@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Benchmark of the cascade-inference hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
+
+A "step" is one pass of the whole path (pyramid -> 3 cascade stages with compaction and fused
+re-crop -> groupRectangles) over one batch of B synthetic 640x480 frames with random-init
+(Xavier) weights of the reference architecture: BASELINE config 2, batched.  Prints ONE JSON line.
+
+  value      frames/s with the frame batch already resident in HBM (device-timed, CUDA events)
+  e2e        the same metric through the public API (InferenceCascadeApp.run_inference_on_images)
+             with HOST frames: pinned H2D copy and D2H of the boxes inside the timed region
+  roofline   the dominant kernel (tcgen05 split-fp16 fc1), timed live with CUDA events on its stream
+  cpu_baseline  the oracle port (oracle/cascade.py: per-window Python extraction + Pillow + cv2 +
+             torch-CPU fp32 stage nets) on the host cores, bounded sample
+
+`--impl reference` times that CPU port alone (TensorFlow 1.4, the reference's own runtime, cannot
+be installed: no wheel for py3.12, no network) on rank 0 and prints the line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "cascade frames/sec at 640x480 full pyramid"
+UNIT = "frames/s"
+FRAME_H, FRAME_W = 480, 640
+WINDOWS_PER_FRAME = 5061
+FLOPS_PER_WINDOW = [4969472, 19873792, 79484928]       # SURVEY.md §8a (2*MAC), stages 0/1/2
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_time(n_frames_max: int, budget_s: float):
+    """Oracle port on the host cores: whole path per frame.  Returns (frames/s, frames timed, cores)."""
+    import torch
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights = synth.xavier_cascade()
+    cfg = oc.Config()
+    done, t_total = 0, 0.0
+    for j in range(n_frames_max):
+        fr = synth.synth_frame(FRAME_H, FRAME_W, j)
+        t0 = time.perf_counter()
+        oc.run_cascade([fr], weights, cfg, dtype=torch.float32, arith="lib")
+        t_total += time.perf_counter() - t0
+        done += 1
+        if t_total > budget_s:
+            break
+    return done / t_total, done, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    fps, done, cores = cpu_port_time(steps + min(args.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": 0, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: 640x480 synthetic frame, full pyramid (factor 1.1, "
+                                   "min_window_length 0.075, 5061 windows), 3-stage 12/24/48 cascade, Xavier weights, "
+                                   "thresholds 0.5, groupRectangles; one frame per step"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d frame(s), whole path, torch-CPU fp32 + Pillow + cv2 (TensorFlow 1.4 not installable)" % done},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=16, help="frames per step and per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fc1", default="tensor", choices=["tensor", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rapidobjectdetectionusingcascadedcnns_b200 as pkg
+    from rapidobjectdetectionusingcascadedcnns_b200 import _lib, synth
+    from rapidobjectdetectionusingcascadedcnns_b200 import dist as rdist
+    from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    B = args.frames
+    pkg.cf.reset()
+    pkg.cf.set("fc1_impl", args.fc1)
+
+    # this rank's frames (weak scaling: B frames per GPU and step; seeds differ per rank)
+    host_frames = [synth.synth_frame(FRAME_H, FRAME_W, rank * B + j) for j in range(B)]
+    weights = synth.xavier_cascade()
+    models = [pkg.StageModel(w) for w in weights]
+    app = pkg.InferenceCascadeApp("bench", stage_models=models, device=local_rank)
+    app._init_tf()
+    eng: CascadeEngine = app._engine
+    infos = [pkg.ArrayImageInfo(f, "bench_r%d_%d.png" % (rank, j)) for j, f in enumerate(host_frames)]
+    d_frames = torch.from_numpy(np.stack(host_frames)).to(dev)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(res):
+        if world > 1:
+            rows = np.column_stack([res.frame + rank * B, res.boxes, res.conf]).astype(np.float64).reshape(-1, 6)
+            rdist.gather_detections(rows, dev)
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed (untimed) in between."""
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            barrier()
+            total += a.elapsed_time(b)
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    last = {}
+
+    def step_resident():
+        res = eng.run_frames(d_frames)
+        gather(res)
+        last["res"] = res
+
+    def step_e2e():
+        out = app.run_inference_on_images(infos, merge=True)
+        last["out"] = out
+
+    for _ in range(warmup):
+        step_resident()
+    barrier()
+    L = _lib.lib()
+    L.rodc_profile_enable(1)
+    eng.kernel_launches = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    launches = eng.kernel_launches
+    import ctypes as C
+    fc1_ms, fc1_fl, fc1_n = C.c_double(), C.c_double(), C.c_int64()
+    L.rodc_profile_collect(C.byref(fc1_ms), C.byref(fc1_fl), C.byref(fc1_n))
+    L.rodc_profile_enable(0)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        res = last["res"]
+        frames_total = B * world * args.steps
+        value = frames_total / (ms_total / 1000.0)
+        e2e = frames_total / (ms_e2e / 1000.0)
+        peak_tf, peak_hbm, which = measured_peaks()
+        mma_per_product = 3 if args.fc1 == "tensor" else 1
+        achieved = fc1_fl.value / (fc1_ms.value / 1000.0) / 1e12 if fc1_ms.value > 0 else 0.0
+        peak = peak_tf / 3.0
+        n_boxes = int(sum(len(p) for p in last["out"]))
+        d2h = int(res.boxes.shape[0]) * 6 * 4 + 8 * (len(res.stage_kept) + 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fc1: fp16x2-split operands, 3 tcgen05 MMAs, fp32 accumulate)" if args.fc1 == "tensor" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 2 batched: %d synthetic 640x480 frames per GPU and step, full pyramid "
+                                   "(factor 1.1, min_window_length 0.075, 24 levels, 5061 windows/frame), 3-stage 12/24/48 "
+                                   "cascade with bottleneck reuse, Xavier random-init weights, thresholds 0.5, "
+                                   "groupRectangles(min_neighbors=1)" % B,
+                       "frames_per_step_per_gpu": B, "l2": "256 MiB flush buffer written between timed steps",
+                       "fc1_impl": args.fc1, "parallelism": "image-sharded replicas x%d, NCCL all-gather of detections" % world},
+            "windows_per_s": value * WINDOWS_PER_FRAME,
+            "stage_in": res.stage_in, "stage_kept": res.stage_kept,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * FRAME_H * FRAME_W * 3,
+                    "d2h_bytes_per_step": d2h, "boxes_per_step": n_boxes, "api": "InferenceCascadeApp.run_inference_on_images(merge=True)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "rodc::tc::fc1_tc_kernel" if args.fc1 == "tensor" else "rodc::fc1_simt_kernel",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "%s bf16_tflops_sustained / 3 (each product = 3 fp16 MMAs)" % which,
+                         "launches": int(fc1_n.value), "avg_launch_ms": fc1_ms.value / max(int(fc1_n.value), 1),
+                         "share_of_step": fc1_ms.value / ms_total if ms_total else None,
+                         "mma_per_product": mma_per_product},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            fps, done, cores = cpu_port_time(3, budget_s=20.0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d frame(s) of the same workload, whole path (oracle/cascade.py: Python "
+                                              "extraction loops + Pillow + cv2 + torch-CPU fp32)" % done}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,14 @@ int64_t rodc_group_scratch_bytes(int64_t k, int n_frames);
 int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
                           int32_t* out, int64_t* out_count, void* scratch, void* stream);
 
+/* ---------------------------------------------------------------- measurement hook
+ * When enabled, every fc1 launch (the dominant kernel) is bracketed by cudaEvents on the stream it
+ * is launched on.  rodc_profile_collect synchronises those events and returns the summed device
+ * time, the algorithmic FLOPs (2*m*K*N per launch) and the launch count since the last collect.
+ * This is the library's only process-wide state; it is off by default. */
+int rodc_profile_enable(int on);
+int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 rodc_stage::~rodc_stage() {
     float* f[] = {conv_w, conv_b, fc1_w, fc1_b, fc2_w, fc2_b};
@@ -61,9 +62,53 @@ static int pow2_headroom(double bound, double limit) {
     return e;
 }
 
+// ---- measurement hook (off by default)
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_pending = nullptr;
+
+void profile_begin(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    cudaEventRecord(a, st);
+    g_prof_pending = a;
+}
+
+void profile_end(cudaStream_t st, double flops) {
+    if (!g_prof_on || !g_prof_pending) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(b, st);
+    g_prof.push_back({g_prof_pending, b, flops});
+    g_prof_pending = nullptr;
+}
+
 }  // namespace rodc
 
 using namespace rodc;
+
+extern "C" int rodc_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return RODC_OK;
+}
+
+extern "C" int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches) {
+    double ms = 0.0, fl = 0.0;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        RODC_CUDA(cudaEventSynchronize(r.b));
+        RODC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; fl += r.flops;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    if (fc1_ms) *fc1_ms = ms;
+    if (fc1_flops) *fc1_flops = fl;
+    if (fc1_launches) *fc1_launches = (int64_t)g_prof.size();
+    g_prof.clear();
+    return RODC_OK;
+}
 
 extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, int n_prev,
                                  const float* conv_w, const float* conv_b,
@@ -144,12 +189,16 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         if (impl == RODC_IMPL_SIMT) {
             float* feat = reinterpret_cast<float*>(workspace);
             if ((rc = launch_features(s, sd, first + c0, m, feat, nullptr, nullptr, st))) return rc;
+            profile_begin(st);
             if ((rc = launch_fc1_simt(s, feat, m, bott, ld_bott, st))) return rc;
+            profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         } else {
             __half* hi = reinterpret_cast<__half*>(workspace);
             __half* lo = hi + m * s->K;
             if ((rc = launch_features(s, sd, first + c0, m, nullptr, hi, lo, st))) return rc;
+            profile_begin(st);
             if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
+            profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         }
     }
     return launch_fc2_softmax(s, bottleneck, ld_bott, n, logits, probs, st);

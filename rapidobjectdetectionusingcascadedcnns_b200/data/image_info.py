@@ -1,0 +1,85 @@
+"""Image access for the hot path (the slice of `data/image_info.py:197-262` that inference uses).
+
+``ImageInfo`` objects only need ``raw_original(cache)``, ``path_original``, ``full_key``,
+``img_height_original`` / ``img_width_original`` and ``clear_raw_img_cache()``; the reference's
+own ``ImageInfo`` satisfies that, and so do the two classes below.  The per-scale cache of
+``raw_scaled`` is gone: pyramid levels are built on the GPU from the original frame.
+"""
+import os
+
+import numpy as np
+
+
+class ArrayImageInfo:
+    """An in-memory ``[H,W,3]`` uint8 frame (synthetic frames, video streams)."""
+
+    def __init__(self, array: np.ndarray, key: str, dataset_key: str = "memory"):
+        a = np.asarray(array)
+        if a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8:
+            raise ValueError("expected an [H,W,3] uint8 array")
+        self._array = np.ascontiguousarray(a)
+        self._key = key
+        self._dataset_key = dataset_key
+
+    @property
+    def path_original(self) -> str:
+        return self._key
+
+    path_resized = path_original
+
+    @property
+    def basename(self) -> str:
+        return os.path.basename(self._key)
+
+    @property
+    def dataset_key(self) -> str:
+        return self._dataset_key
+
+    @property
+    def full_key(self) -> str:
+        return self._dataset_key + "/" + self._key
+
+    def raw_original(self, cache=False) -> np.ndarray:
+        return self._array
+
+    @property
+    def img_height_original(self) -> int:
+        return int(self._array.shape[0])
+
+    @property
+    def img_width_original(self) -> int:
+        return int(self._array.shape[1])
+
+    def clear_raw_img_cache(self):
+        pass
+
+
+class FileImageInfo(ArrayImageInfo):
+    """A file on disk, decoded ONCE to RGB uint8 (the reference re-decodes it for every
+    pyramid scale, `data/image_info.py:228-240`)."""
+
+    def __init__(self, path_original: str, dataset_key: str = "files"):
+        self._path = path_original
+        self._key = path_original
+        self._dataset_key = dataset_key
+        self._array = None
+
+    def raw_original(self, cache=False) -> np.ndarray:
+        if self._array is None:
+            from PIL import Image
+            arr = np.asarray(Image.open(self._path).convert("RGB"), dtype=np.uint8)
+            if not cache:
+                return arr
+            self._array = np.ascontiguousarray(arr)
+        return self._array
+
+    @property
+    def img_height_original(self) -> int:
+        return int(self.raw_original(True).shape[0])
+
+    @property
+    def img_width_original(self) -> int:
+        return int(self.raw_original(True).shape[1])
+
+    def clear_raw_img_cache(self):
+        self._array = None

