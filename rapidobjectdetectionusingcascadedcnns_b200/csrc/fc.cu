@@ -17,11 +17,13 @@ __global__ void __launch_bounds__(256) fc1_simt_kernel(const float* __restrict__
     const int64_t m0 = (int64_t)blockIdx.y * 128;
     const int n0 = blockIdx.x * 128;
     const int ty = tid >> 4, tx = tid & 15;
-    float acc[8][8];
+    // two-level blocked summation (like Eigen's GEMM and like the tensor path): `acc` sums one block
+    // of 64 k, `tot` sums the blocks -- keeps the fp32 rounding error ~sqrt(K/64) instead of ~sqrt(K)
+    float acc[8][8], tot[8][8];
     #pragma unroll
     for (int i = 0; i < 8; ++i)
         #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
     const int a_row = tid >> 1, a_kq = (tid & 1) * 4;
     const int b_k = tid >> 5, b_n = (tid & 31) * 4;
     const bool a_ok = (m0 + a_row) < m;
@@ -46,6 +48,12 @@ __global__ void __launch_bounds__(256) fc1_simt_kernel(const float* __restrict__
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
+        if ((k0 & 63) == 56 || k0 + 8 >= K) {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i)
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+        }
     }
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -53,7 +61,7 @@ __global__ void __launch_bounds__(256) fc1_simt_kernel(const float* __restrict__
         if (r >= m) continue;
         float* o = out + r * ld_out + n0 + tx * 8;
         #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaxf(acc[i][j] + __ldg(bias + n0 + tx * 8 + j), 0.f);
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(tot[i][j] + __ldg(bias + n0 + tx * 8 + j), 0.f);
     }
 }
 

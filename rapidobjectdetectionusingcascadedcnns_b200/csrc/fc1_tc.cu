@@ -10,15 +10,16 @@
 //       A_hi*B_lo + A_lo*B_hi + A_hi*B_hi           (the dropped lo*lo term is < 2^-22 relative)
 // i.e. fp32-grade products at 1/3 of the fp16 tensor peak instead of a CUDA-core SGEMM.
 //
-// Structure (one CTA per 128 x 256 output tile, 192 threads):
+// Structure (one CTA per 128 x 256 output tile, 320 threads):
 //   warp 0      TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, 4 tiles per stage
 //                              (A_hi, A_lo: 128 x 64 fp16; B_hi, B_lo: 256 x 64 fp16 = 96 KB/stage)
 //   warp 1      TMEM alloc + MMA issuer (one lane): 4 k-steps x 3 tcgen05.mma (M128 N256 K16) per
 //               stage, tcgen05.commit -> empty barrier (smem slot free) / tmem_full barrier
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (one TMEM lane quarter each) -> scale 2^-(ea+ew),
-//               + bias, ReLU -> fp32 rows of the concat buffer
+//   warps 2..9  epilogue: drain each finished TMEM chunk with tcgen05.ld 32x32b into fp32 register
+//               accumulators (RN adds), finally scale 2^-(ea+ew), + bias, ReLU -> concat buffer rows
 #include "stage.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace rodc {
 namespace tc {
@@ -29,8 +30,9 @@ constexpr int A_TILE = BM * BK * 2;                 // 16 KB
 constexpr int B_TILE = BN * BK * 2;                 // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TMEM_COLS = 512;                 // two 128 x 256 fp32 accumulator buffers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -94,23 +96,41 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, M128 x N256.
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Accumulation.  The tensor core adds into its fp32 TMEM accumulator with truncation (measured on
+// B200: error grows linearly with K, ~0.5 ulp per MMA step, 3e-4 relative at K = 73728).  The K loop
+// is therefore cut into chunks of `kc` k-blocks: each chunk accumulates into one of two TMEM buffers
+// starting from zero (inside a k-block the eight small hi*lo / lo*hi MMAs come first, so only the
+// four hi*hi steps add onto a non-trivial partial sum), and the eight epilogue warps drain the
+// finished buffer with tcgen05.ld and add it into fp32 REGISTER accumulators with round-to-nearest
+// while the MMA warp already fills the other buffer -- the two-level blocked summation Eigen's GEMM
+// uses on the CPU, so the result carries the same kind of error as the reference's own fp32 path.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-              const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, float out_scale) {
+              const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
+              float out_scale) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] tmem_full; then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    // bars: [0,2) smem full, [2,4) smem empty, [4,6) tmem full, [6,8) tmem empty; then the TMEM base address
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + STAGES;
+    uint64_t* bar_tfull = bars + 2 * STAGES;
+    uint64_t* bar_tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x & 1, m_tile = blockIdx.x >> 1;
     const int m0 = m_tile * BM, n0 = n_tile * BN;
+    const int num_chunks = (num_kb + kc - 1) / kc;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[STAGES + s]), 1); }
-        mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_tfull[b]), 1); mbar_init(smem_u32(&bar_tempty[b]), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -131,8 +151,8 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1u);
-                const uint32_t full = smem_u32(&bars[s]);
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[s]);
                 mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
                 tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
@@ -146,45 +166,66 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(smem_u32(&bars[s]), ph);
+                const int chunk = kb / kc, kin = kb - chunk * kc;
+                const int buf = chunk & 1;
+                if (kin == 0) mbar_wait(smem_u32(&bar_tempty[buf]), ((uint32_t)(chunk >> 1) & 1u) ^ 1u);   // buffer drained
+                mbar_wait(smem_u32(&bar_full[s]), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
                 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint32_t koff = k * UMMA_K * 2;             // bytes along K inside the 128 B swizzle row
+                for (int k = 0; k < BK / UMMA_K; ++k) {                // the small cross terms first
+                    const uint32_t koff = k * UMMA_K * 2;
                     const uint64_t a_hi = smem_desc_sw128(base + koff);
                     const uint64_t a_lo = smem_desc_sw128(base + A_TILE + koff);
                     const uint64_t b_hi = smem_desc_sw128(base + 2 * A_TILE + koff);
                     const uint64_t b_lo = smem_desc_sw128(base + 2 * A_TILE + B_TILE + koff);
-                    umma_f16(tmem_base, a_hi, b_lo, IDESC, (kb | k) != 0);
-                    umma_f16(tmem_base, a_lo, b_hi, IDESC, 1u);
-                    umma_f16(tmem_base, a_hi, b_hi, IDESC, 1u);
+                    umma_f16(acc, a_hi, b_lo, IDESC, (kin | k) != 0);
+                    umma_f16(acc, a_lo, b_hi, IDESC, 1u);
                 }
-                umma_commit(smem_u32(&bars[STAGES + s]));            // smem slot free once these MMAs retire
+                #pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {                // then the dominant hi*hi terms
+                    const uint32_t koff = k * UMMA_K * 2;
+                    umma_f16(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), IDESC, 1u);
+                }
+                umma_commit(smem_u32(&bar_empty[s]));                  // smem slot free once these MMAs retire
+                if (kin == kc - 1 || kb == num_kb - 1) umma_commit(smem_u32(&bar_tfull[buf]));   // chunk complete
             }
-            umma_commit(smem_u32(&bars[2 * STAGES]));                // accumulator complete
         }
     } else {
-        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
-        const int q = warp & 3;
-        mbar_wait(smem_u32(&bars[2 * STAGES]), 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
-        float* orow = out + (int64_t)row * ld_out + n0;
-        #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            if (row < m) {
+        // epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+        const int q = warp & 3, hcol = (warp - 2) >> 2;
+        float acc[128];
+        #pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(chunk >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hcol * 128);
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
                 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = fmaxf(fmaf(v[j + 0], out_scale, __ldg(bias + n0 + c + j + 0)), 0.f);
-                    o.y = fmaxf(fmaf(v[j + 1], out_scale, __ldg(bias + n0 + c + j + 1)), 0.f);
-                    o.z = fmaxf(fmaf(v[j + 2], out_scale, __ldg(bias + n0 + c + j + 2)), 0.f);
-                    o.w = fmaxf(fmaf(v[j + 3], out_scale, __ldg(bias + n0 + c + j + 3)), 0.f);
-                    *reinterpret_cast<float4*>(orow + c + j) = o;
-                }
+                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        }
+        const int row = m0 + q * 32 + lane;
+        if (row < m) {
+            float* orow = out + (int64_t)row * ld_out + n0 + hcol * 128;
+            const float* brow = bias + n0 + hcol * 128;
+            #pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+                float4 o;
+                o.x = fmaxf(fmaf(acc[j + 0], out_scale, __ldg(brow + j + 0)), 0.f);
+                o.y = fmaxf(fmaf(acc[j + 1], out_scale, __ldg(brow + j + 1)), 0.f);
+                o.z = fmaxf(fmaf(acc[j + 2], out_scale, __ldg(brow + j + 2)), 0.f);
+                o.w = fmaxf(fmaf(acc[j + 3], out_scale, __ldg(brow + j + 3)), 0.f);
+                *reinterpret_cast<float4*>(orow + j) = o;
             }
         }
     }
@@ -225,6 +266,17 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
     return RODC_OK;
 }
 
+// k-blocks (of 64) accumulated inside the tensor core before a drain; RODC_FC1_KC overrides (tests)
+static int fc1_chunk_kblocks() {
+    static int kc = 0;
+    if (kc == 0) {
+        const char* e = getenv("RODC_FC1_KC");
+        kc = e ? atoi(e) : 1;
+        if (kc < 1) kc = 1;
+    }
+    return kc;
+}
+
 }  // namespace tc
 
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
@@ -243,7 +295,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
     const unsigned tiles = (unsigned)((m + BM - 1) / BM) * 2u;
     const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
     fc1_tc_kernel<<<tiles, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                      (int)(s->K / BK), out_scale);
+                                                      (int)(s->K / BK), fc1_chunk_kblocks(), out_scale);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
