@@ -15,6 +15,8 @@
 // Output: fp32 features (SIMT fc1 / tests) or the split-fp16 A operand of the tensor fc1:
 //   f * 2^a_exp = hi + lo  (hi, lo fp16; 22 significant bits), planes [n, K] K-contiguous.
 #include "stage.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace rodc {
 
@@ -247,6 +249,204 @@ features_kernel(SrcDev src, int64_t first, int64_t n, int S, int R,
     }
 }
 
+// ------------------------------------------------------------------ feature kernel v2 (tensor-core conv)
+// The 3x3x3 -> 32 convolution is a [pixels x 48] x [48 x 32] GEMM per window: K = 3 filter rows x
+// (4 pixels x 4 channels), where the 4th pixel / 4th channel carry zero weights so that the A row of
+// a pixel is ONE contiguous 32-byte run of the fp16 input staged as [P][P][4] -- the im2col matrix is
+// never built.  u8 pixels are exact in fp16; the fp32 weights are split w * 2^e = hi + lo (fp16), so
+// each product is exact and the conv costs 24 mma.sync.m16n8k16 per 16 pixels instead of 864 FFMA per
+// pixel-row group.  (Legacy warp-level MMA is the right tool here: N = 32, K = 48 tiles are far too
+// small to feed tcgen05, and the conv is < 6 % of the stage FLOPs.)
+// Pooling is register blocked (each thread walks 4 rows x 4 pixels x 2 channels with a sliding window
+// of horizontal maxima), the CTA loops over windows so the weight fragments are loaded once.
+constexpr int CS = 40;            // floats per pixel in the conv buffer (32 + pad: conflict-free float2 stores)
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int OUT_SPLIT>
+__global__ void __launch_bounds__(FEAT_THREADS)
+features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S, int R,
+                    const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
+                    float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    constexpr int C = 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = S + 2;
+    const int inh_halves = (P * P * 4 + 16 + 7) & ~7;
+    __half* inh = reinterpret_cast<__half*>(smem_raw);                         // [P][P][4] fp16, zero border
+    float* cbuf = reinterpret_cast<float*>(smem_raw + (size_t)inh_halves * 2); // [R+2][P][CS]
+    int* tabs = reinterpret_cast<int*>(cbuf + (R + 2) * P * CS);               // [6][S]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    // weight fragments of the whole conv (hi and lo planes) + biases of this thread's channels
+    uint32_t bf[3][4][2][2];
+    #pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+        #pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(conv_frag) + ((ky * 4 + nt) * 2 + h) * 32 + lane);
+                bf[ky][nt][h][0] = v.x; bf[ky][nt][h][1] = v.y;
+            }
+    float2 bias2[4];
+    #pragma unroll
+    for (int nt = 0; nt < 4; ++nt) bias2[nt] = make_float2(__ldg(conv_b + 8 * nt + 2 * t), __ldg(conv_b + 8 * nt + 2 * t + 1));
+
+    for (int i = tid; i < (R + 2) * P * CS; i += FEAT_THREADS) cbuf[i] = 0.f;   // borders stay zero forever
+
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
+        const int64_t w = first + wrel;
+        __syncthreads();                                      // previous window fully consumed
+        // ---- 1. stage the window as zero-padded fp16 [P][P][4]
+        {
+            uint4* z = reinterpret_cast<uint4*>(inh);
+            for (int i = tid; i < inh_halves / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        Crop crop;
+        if (src.kind == RODC_SRC_RECROP) { crop = make_crop(src, w); fill_recrop_tables(crop, S, tabs); }
+        __syncthreads();
+        if (src.kind == RODC_SRC_RECROP) {
+            for (int i = tid; i < S * S; i += FEAT_THREADS) {
+                const int y = i / S, x = i - y * S;
+                int px[3];
+                recrop_pixel(crop, S, tabs, y, x, px);
+                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
+                d[0] = __halves2half2(__int2half_rn(px[0]), __int2half_rn(px[1]));
+                d[1] = __halves2half2(__int2half_rn(px[2]), __int2half_rn(0));
+            }
+        } else {
+            const uint8_t* p; int pitch;
+            if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+            else {
+                const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
+                const int32_t* wr = src.win + j * 8;
+                const LevelInfo& lv = src.levels[wr[0]];
+                p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+                pitch = lv.w * 3;
+            }
+            for (int i = tid; i < S * S; i += FEAT_THREADS) {
+                const int y = i / S, x = i - y * S;
+                const uint8_t* q = p + (int64_t)y * pitch + x * 3;
+                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
+                d[0] = __halves2half2(__int2half_rn((int)q[0]), __int2half_rn((int)q[1]));
+                d[1] = __halves2half2(__int2half_rn((int)q[2]), __int2half_rn(0));
+            }
+        }
+        __syncthreads();
+
+        float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C;
+        __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C : nullptr;
+        __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C : nullptr;
+
+        for (int r0 = 0; r0 < S; r0 += R) {
+            // ---- 2. conv + bias + ReLU of rows r0-1 .. r0+R  ->  cbuf rows 0 .. R+1 (mma.sync)
+            const int npix = (R + 2) * S;
+            for (int tile = warp; tile * 16 < npix; tile += FEAT_THREADS / 32) {
+                int pa = tile * 16 + g, pb = pa + 8;
+                const bool va = pa < npix, vb = pb < npix;
+                pa = va ? pa : 0; pb = vb ? pb : 0;
+                const int rya = pa / S, xa = pa - rya * S, ryb = pb / S, xb = pb - ryb * S;
+                const int ya = r0 - 1 + rya, yb = r0 - 1 + ryb;
+                const bool ina = va && ya >= 0 && ya < S, inb = vb && yb >= 0 && yb < S;
+                const int yca = min(max(ya, 0), S - 1), ycb = min(max(yb, 0), S - 1);
+                const uint32_t* rowa = reinterpret_cast<const uint32_t*>(inh + ((yca * P) + xa) * 4) + t;
+                const uint32_t* rowb = reinterpret_cast<const uint32_t*>(inh + ((ycb * P) + xb) * 4) + t;
+                float acc[4][4];
+                #pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+                #pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t a0 = rowa[ky * P * 2], a2 = rowa[ky * P * 2 + 4];
+                    const uint32_t a1 = rowb[ky * P * 2], a3 = rowb[ky * P * 2 + 4];
+                    #pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        mma16816(acc[nt], a0, a1, a2, a3, bf[ky][nt][1][0], bf[ky][nt][1][1]);     // lo weights first
+                        mma16816(acc[nt], a0, a1, a2, a3, bf[ky][nt][0][0], bf[ky][nt][0][1]);
+                    }
+                }
+                float* da = cbuf + ((rya * P) + xa + 1) * CS + 2 * t;
+                float* db = cbuf + ((ryb * P) + xb + 1) * CS + 2 * t;
+                #pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    if (va) *reinterpret_cast<float2*>(da + 8 * nt) = ina
+                        ? make_float2(fmaxf(fmaf(acc[nt][0], conv_scale, bias2[nt].x), 0.f), fmaxf(fmaf(acc[nt][1], conv_scale, bias2[nt].y), 0.f))
+                        : make_float2(0.f, 0.f);
+                    if (vb) *reinterpret_cast<float2*>(db + 8 * nt) = inb
+                        ? make_float2(fmaxf(fmaf(acc[nt][2], conv_scale, bias2[nt].x), 0.f), fmaxf(fmaf(acc[nt][3], conv_scale, bias2[nt].y), 0.f))
+                        : make_float2(0.f, 0.f);
+                }
+            }
+            __syncthreads();
+            // ---- 3. maxpool 3x3 (register blocked: 4 rows x 4 pixels x 2 channels per item) + store
+            const int rows = min(R, S - r0);
+            const int XG = S >> 2, SEG = (rows + 3) >> 2;
+            const int items = SEG * XG * 16;
+            for (int it = tid; it < items; it += FEAT_THREADS) {
+                const int cp = it & 15;
+                const int rest = it >> 4;
+                const int xg = rest % XG, seg = rest / XG;
+                const int rbeg = seg * 4, rend = min(rbeg + 4, rows);
+                float2 hprev[4], hcur[4];
+                // horizontal maxima of cbuf row `rr` (strip-local conv row index) for the 4 pixels
+                auto hmax = [&](int rr, float2 (&h)[4]) {
+                    const float2* c0 = reinterpret_cast<const float2*>(cbuf + ((rr * P) + xg * 4) * CS + 2 * cp);
+                    float2 v[6];
+                    #pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] = c0[q * (CS / 2)];
+                    #pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        h[px].x = fmaxf(fmaxf(v[px].x, v[px + 1].x), v[px + 2].x);
+                        h[px].y = fmaxf(fmaxf(v[px].y, v[px + 1].y), v[px + 2].y);
+                    }
+                };
+                hmax(rbeg, hprev);          // conv row above the first pooled row
+                hmax(rbeg + 1, hcur);
+                for (int r = rbeg; r < rend; ++r) {
+                    float2 hnext[4];
+                    hmax(r + 2, hnext);
+                    #pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        float2 m;
+                        m.x = fmaxf(fmaxf(hprev[px].x, hcur[px].x), hnext[px].x);
+                        m.y = fmaxf(fmaxf(hprev[px].y, hcur[px].y), hnext[px].y);
+                        const int64_t k = ((int64_t)(r0 + r) * S + xg * 4 + px) * C + 2 * cp;
+                        if (OUT_SPLIT) {
+                            const float sx = m.x * a_scale, sy = m.y * a_scale;            // exact: power of two
+                            const __half2 h2 = __floats2half2_rn(sx, sy);
+                            const float2 hf = __half22float2(h2);
+                            *reinterpret_cast<__half2*>(oh + k) = h2;
+                            *reinterpret_cast<__half2*>(ol + k) = __floats2half2_rn(sx - hf.x, sy - hf.y);
+                        } else {
+                            *reinterpret_cast<float2*>(of + k) = m;
+                        }
+                        hprev[px] = hcur[px]; hcur[px] = hnext[px];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static size_t feat2_smem_bytes(int S, int R) {
+    const int P = S + 2;
+    const size_t inh = (size_t)((P * P * 4 + 16 + 7) & ~7) * 2;
+    return inh + (size_t)(R + 2) * P * CS * 4 + (size_t)6 * S * 4;
+}
+
+static int pick_rows2(int S) {
+    for (int R = S; R > 4; R -= 4)
+        if (feat2_smem_bytes(S, R) <= 100 * 1024) return R;
+    return 4;
+}
+
 static size_t feat_smem_bytes(int S, int R) {
     const int P = S + 2;
     return (size_t)((P * P * 3 + 3) & ~3) * 4 + (size_t)(R + 2) * P * 32 * 4 + (size_t)6 * S * 4;
@@ -285,21 +485,44 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     return RODC_OK;
 }
 
+static bool use_legacy_features() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RODC_FEATURES_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
                     float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st) {
     if (n <= 0) return RODC_OK;
     RODC_CHECK_ARG(s->channels == 32, "feature kernel is built for 32 conv channels (got %d)", s->channels);
     RODC_CHECK_ARG((s->in_size & 3) == 0, "stage input size must be a multiple of 4 (got %d)", s->in_size);
     RODC_CHECK_ARG(n < (1ll << 31), "too many windows in one launch");
-    const int S = s->in_size, R = pick_rows(S);
-    const size_t smem = feat_smem_bytes(S, R);
+    const int S = s->in_size;
     const float a_scale = ldexpf(1.f, s->a_exp);
+    if (use_legacy_features()) {          // CUDA-core conv (first implementation, kept as a cross-check)
+        const int R = pick_rows(S);
+        const size_t smem = feat_smem_bytes(S, R);
+        if (out_f32) {
+            RODC_CUDA(cudaFuncSetAttribute(features_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            features_kernel<0><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, out_f32, nullptr, nullptr);
+        } else {
+            RODC_CUDA(cudaFuncSetAttribute(features_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            features_kernel<1><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, nullptr, out_hi, out_lo);
+        }
+        RODC_LAUNCH_CHECK();
+        return RODC_OK;
+    }
+    const int R = pick_rows2(S);
+    const size_t smem = feat2_smem_bytes(S, R);
+    const float conv_scale = ldexpf(1.f, -s->c_exp);
+    // persistent-style grid: two CTAs per SM, each loops over windows
+    const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
     if (out_f32) {
-        RODC_CUDA(cudaFuncSetAttribute(features_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        features_kernel<0><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, out_f32, nullptr, nullptr);
+        RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        features_mma_kernel<0><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_frag, s->conv_b, conv_scale, a_scale, out_f32, nullptr, nullptr);
     } else {
-        RODC_CUDA(cudaFuncSetAttribute(features_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        features_kernel<1><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, nullptr, out_hi, out_lo);
+        RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        features_mma_kernel<1><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_frag, s->conv_b, conv_scale, a_scale, nullptr, out_hi, out_lo);
     }
     RODC_LAUNCH_CHECK();
     return RODC_OK;

@@ -12,6 +12,7 @@ rodc_stage::~rodc_stage() {
     for (float* p : f) if (p) cudaFree(p);
     if (fc1_hi) cudaFree(fc1_hi);
     if (fc1_lo) cudaFree(fc1_lo);
+    if (conv_frag) cudaFree(conv_frag);
 }
 
 namespace rodc {
@@ -141,6 +142,42 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
     for (size_t i = 0; i < nfc1; ++i) { double a = fabs((double)fc1_w[i]); if (a > wmax) wmax = a; }
     s->a_exp = pow2_headroom(fbound, 32768.0);
     s->w_exp = pow2_headroom(wmax, 16384.0);
+    // conv weights as mma.sync.m16n8k16 B fragments (features.cu): K index j of filter row ky is
+    // (kx = j / 4, ci = j % 4); kx == 3 and ci == 3 are zero padding.  w * 2^c_exp = hi + lo (fp16).
+    {
+        double cmax = 0.0;
+        for (size_t i = 0; i < nconv; ++i) { double a = fabs((double)conv_w[i]); if (a > cmax) cmax = a; }
+        s->c_exp = pow2_headroom(cmax, 16384.0);
+        const float cs = ldexpf(1.f, s->c_exp);
+        std::vector<uint32_t> frag((size_t)3 * 4 * 2 * 32 * 2, 0u);
+        auto wval = [&](int ky, int j, int nn) -> float {
+            const int kx = j >> 2, ci = j & 3;
+            if (kx > 2 || ci > 2) return 0.f;
+            return conv_w[((ky * 3 + kx) * 3 + ci) * conv_channels + nn] * cs;
+        };
+        auto halfbits = [](float v, int lo) -> uint32_t {
+            const __half h = __float2half_rn(v);
+            __half r = h;
+            if (lo) r = __float2half_rn(v - __half2float(h));
+            unsigned short b; memcpy(&b, &r, 2);
+            return (uint32_t)b;
+        };
+        for (int ky = 0; ky < 3; ++ky)
+            for (int nt = 0; nt < 4; ++nt)
+                for (int h = 0; h < 2; ++h)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int gg = lane >> 2, tt = lane & 3, nn = nt * 8 + gg;
+                        for (int r = 0; r < 2; ++r) {
+                            const int j0 = 2 * tt + 8 * r;
+                            const uint32_t lo16 = halfbits(wval(ky, j0, nn), h), hi16 = halfbits(wval(ky, j0 + 1, nn), h);
+                            frag[((((size_t)(ky * 4 + nt) * 2 + h) * 32) + lane) * 2 + r] = lo16 | (hi16 << 16);
+                        }
+                    }
+        if (cudaMalloc(&s->conv_frag, frag.size() * 4) != cudaSuccess ||
+            cudaMemcpy(s->conv_frag, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("upload of the conv fragments failed"); delete s; return RODC_ERR_NOMEM;
+        }
+    }
     cudaError_t e1 = cudaMalloc(&s->fc1_hi, nfc1 * sizeof(__half));
     cudaError_t e2 = cudaMalloc(&s->fc1_lo, nfc1 * sizeof(__half));
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("cudaMalloc of the split fc1 weights failed"); delete s; return RODC_ERR_NOMEM; }

@@ -19,6 +19,8 @@ struct rodc_stage {
     // split-fp16 fc1 weights for the tensor path: W * 2^w_exp = hi + lo, stored [fc1, K] (K-major)
     __half* fc1_hi = nullptr;
     __half* fc1_lo = nullptr;
+    uint32_t* conv_frag = nullptr;  // mma.sync B fragments of the conv: [3 ky][4 nt][hi,lo][32 lanes][2] half2
+    int c_exp = 0;              // conv weights are scaled by 2^c_exp before the fp16 split
     int a_exp = 0;              // features are scaled by 2^a_exp before the fp16 split
     int w_exp = 0;              // weights  are scaled by 2^w_exp before the fp16 split
     ~rodc_stage();
