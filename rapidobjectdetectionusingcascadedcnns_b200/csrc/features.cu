@@ -268,13 +268,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int OUT_SPLIT>
-__global__ void __launch_bounds__(FEAT_THREADS)
-features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S, int R,
+// ST / RT: compile-time window side and strip height (0 = take the run-time arguments); the three
+// reference sizes 12 / 24 / 48 get fully specialised code (constant divisions, unrolled pooling).
+template <int OUT_SPLIT, int ST, int RT>
+__global__ void __launch_bounds__(FEAT_THREADS, 2)
+features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
                     const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
                     float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
     constexpr int C = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = ST ? ST : S_rt;
+    const int R = RT ? RT : R_rt;
     const int P = S + 2;
     const int inh_halves = (P * P * 4 + 16 + 7) & ~7;
     __half* inh = reinterpret_cast<__half*>(smem_raw);                         // [P][P][4] fp16, zero border
@@ -392,41 +396,43 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S, int R,
                 const int cp = it & 15;
                 const int rest = it >> 4;
                 const int xg = rest % XG, seg = rest / XG;
-                const int rbeg = seg * 4, rend = min(rbeg + 4, rows);
-                float2 hprev[4], hcur[4];
-                // horizontal maxima of cbuf row `rr` (strip-local conv row index) for the 4 pixels
-                auto hmax = [&](int rr, float2 (&h)[4]) {
-                    const float2* c0 = reinterpret_cast<const float2*>(cbuf + ((rr * P) + xg * 4) * CS + 2 * cp);
-                    float2 v[6];
-                    #pragma unroll
-                    for (int q = 0; q < 6; ++q) v[q] = c0[q * (CS / 2)];
-                    #pragma unroll
-                    for (int px = 0; px < 4; ++px) {
-                        h[px].x = fmaxf(fmaxf(v[px].x, v[px + 1].x), v[px + 2].x);
-                        h[px].y = fmaxf(fmaxf(v[px].y, v[px + 1].y), v[px + 2].y);
-                    }
-                };
-                hmax(rbeg, hprev);          // conv row above the first pooled row
-                hmax(rbeg + 1, hcur);
-                for (int r = rbeg; r < rend; ++r) {
-                    float2 hnext[4];
-                    hmax(r + 2, hnext);
-                    #pragma unroll
-                    for (int px = 0; px < 4; ++px) {
-                        float2 m;
-                        m.x = fmaxf(fmaxf(hprev[px].x, hcur[px].x), hnext[px].x);
-                        m.y = fmaxf(fmaxf(hprev[px].y, hcur[px].y), hnext[px].y);
-                        const int64_t k = ((int64_t)(r0 + r) * S + xg * 4 + px) * C + 2 * cp;
-                        if (OUT_SPLIT) {
-                            const float sx = m.x * a_scale, sy = m.y * a_scale;            // exact: power of two
-                            const __half2 h2 = __floats2half2_rn(sx, sy);
-                            const float2 hf = __half22float2(h2);
-                            *reinterpret_cast<__half2*>(oh + k) = h2;
-                            *reinterpret_cast<__half2*>(ol + k) = __floats2half2_rn(sx - hf.x, sy - hf.y);
-                        } else {
-                            *reinterpret_cast<float2*>(of + k) = m;
+                const int rbeg = seg * 4, nrow = min(4, rows - rbeg);
+                // horizontal 3-maxima of the six conv rows this item touches (all in registers)
+                float2 h[6][4];
+                #pragma unroll
+                for (int rr = 0; rr < 6; ++rr) {
+                    if (rr < nrow + 2) {
+                        const float2* c0 = reinterpret_cast<const float2*>(cbuf + (((rbeg + rr) * P) + xg * 4) * CS + 2 * cp);
+                        float2 v[6];
+                        #pragma unroll
+                        for (int q = 0; q < 6; ++q) v[q] = c0[q * (CS / 2)];
+                        #pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            h[rr][px].x = fmaxf(fmaxf(v[px].x, v[px + 1].x), v[px + 2].x);
+                            h[rr][px].y = fmaxf(fmaxf(v[px].y, v[px + 1].y), v[px + 2].y);
                         }
-                        hprev[px] = hcur[px]; hcur[px] = hnext[px];
+                    }
+                }
+                #pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r < nrow) {
+                        const int64_t kbase = ((int64_t)(r0 + rbeg + r) * S + xg * 4) * C + 2 * cp;
+                        #pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            float2 m;
+                            m.x = fmaxf(fmaxf(h[r][px].x, h[r + 1][px].x), h[r + 2][px].x);
+                            m.y = fmaxf(fmaxf(h[r][px].y, h[r + 1][px].y), h[r + 2][px].y);
+                            const int64_t k = kbase + px * C;
+                            if (OUT_SPLIT) {
+                                const float sx = m.x * a_scale, sy = m.y * a_scale;            // exact: power of two
+                                const __half2 h2 = __floats2half2_rn(sx, sy);
+                                const float2 hf = __half22float2(h2);
+                                *reinterpret_cast<__half2*>(oh + k) = h2;
+                                *reinterpret_cast<__half2*>(ol + k) = __floats2half2_rn(sx - hf.x, sy - hf.y);
+                            } else {
+                                *reinterpret_cast<float2*>(of + k) = m;
+                            }
+                        }
                     }
                 }
             }
@@ -512,18 +518,28 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
-    const int R = pick_rows2(S);
-    const size_t smem = feat2_smem_bytes(S, R);
     const float conv_scale = ldexpf(1.f, -s->c_exp);
     // persistent-style grid: two CTAs per SM, each loops over windows
     const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
+#define RODC_LAUNCH_FEAT(SPLIT, ST_, RT_, Rv)                                                                              \
+    do {                                                                                                                  \
+        const size_t smem = feat2_smem_bytes(S, Rv);                                                                      \
+        RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<SPLIT, ST_, RT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        features_mma_kernel<SPLIT, ST_, RT_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, Rv, s->conv_frag, s->conv_b, \
+                                                                                conv_scale, a_scale, out_f32, out_hi, out_lo); \
+    } while (0)
     if (out_f32) {
-        RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        features_mma_kernel<0><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_frag, s->conv_b, conv_scale, a_scale, out_f32, nullptr, nullptr);
+        if (S == 12) RODC_LAUNCH_FEAT(0, 12, 12, 12);
+        else if (S == 24) RODC_LAUNCH_FEAT(0, 24, 12, 12);
+        else if (S == 48) RODC_LAUNCH_FEAT(0, 48, 8, 8);
+        else { const int R = pick_rows2(S); RODC_LAUNCH_FEAT(0, 0, 0, R); }
     } else {
-        RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        features_mma_kernel<1><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_frag, s->conv_b, conv_scale, a_scale, nullptr, out_hi, out_lo);
+        if (S == 12) RODC_LAUNCH_FEAT(1, 12, 12, 12);
+        else if (S == 24) RODC_LAUNCH_FEAT(1, 24, 12, 12);
+        else if (S == 48) RODC_LAUNCH_FEAT(1, 48, 8, 8);
+        else { const int R = pick_rows2(S); RODC_LAUNCH_FEAT(1, 0, 0, R); }
     }
+#undef RODC_LAUNCH_FEAT
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
