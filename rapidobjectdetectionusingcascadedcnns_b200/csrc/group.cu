@@ -52,18 +52,25 @@ __global__ void group_init_kernel(int32_t* __restrict__ parent, int32_t* __restr
     }
 }
 
+// Path-halving find: every store writes an ancestor (parents only ever decrease), so concurrent
+// readers stay correct without synchronisation.
 __device__ __forceinline__ int find_root(volatile int32_t* parent, int x) {
-    int cur = x, nxt;
-    while ((nxt = parent[cur]) != cur) cur = nxt;
-    return cur;
+    int cur = x;
+    while (true) {
+        const int p = parent[cur];
+        if (p == cur) return cur;
+        const int gp = parent[p];
+        if (gp != p) parent[cur] = gp;
+        cur = gp;
+    }
 }
 
-__device__ __forceinline__ void unite(int32_t* parent, int a, int b) {
+__device__ __forceinline__ int unite(int32_t* parent, int a, int b) {
     while (true) {
         a = find_root(parent, a); b = find_root(parent, b);
-        if (a == b) return;
+        if (a == b) return a;
         if (a < b) { int t = a; a = b; b = t; }          // a > b: the larger root links under the smaller
-        if (atomicCAS(&parent[a], a, b) == a) return;
+        if (atomicCAS(&parent[a], a, b) == a) return b;
     }
 }
 
@@ -79,16 +86,46 @@ __device__ __forceinline__ int4 load_xywh(const int32_t* cand, int64_t i) {
     return make_int4(c[1], c[2], c[3] - c[1], c[4] - c[2]);       // (x, y, w, h) as _run_nms builds them
 }
 
-// grid: (tiles over candidates); each thread owns candidate i and scans j < i of the same frame.
-__global__ void __launch_bounds__(256) group_union_kernel(const int32_t* __restrict__ cand, int64_t K,
-                                                          const int32_t* __restrict__ seg, int32_t* __restrict__ parent, double eps) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= K) return;
-    const int f = cand[i * 5];
-    const int s0 = seg[f];
-    const int4 ri = load_xywh(cand, i);
-    for (int64_t j = s0; j < i; ++j) {
-        if (similar(ri, load_xywh(cand, j), eps)) unite(parent, (int)i, (int)j);
+// Pair scan, tiled through shared memory.  grid.x = tiles of 256 candidates (global index space);
+// each thread owns candidate i and tests every j < i of the same frame, 256 at a time from smem.
+// An integer prefilter (a superset of the exact predicate for eps <= 0.5) rejects most pairs before
+// the double-precision SimilarRects test; the thread keeps its current root in a register so that
+// already-merged neighbours cost one find and no atomic.
+constexpr int GT = 256;
+__global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restrict__ cand, int64_t K,
+                                                         const int32_t* __restrict__ seg, int32_t* __restrict__ parent, double eps) {
+    __shared__ int4 tile[GT];
+    const int64_t i0 = (int64_t)blockIdx.x * GT;
+    const int64_t i = i0 + threadIdx.x;
+    const bool active = i < K;
+    int4 ri = make_int4(0, 0, 0, 0);
+    int fi = -1;
+    if (active) { ri = load_xywh(cand, i); fi = cand[i * 5]; }
+    // candidates are grouped by frame: this block needs j from the first frame's segment start on
+    const int f_first = cand[i0 * 5];
+    const int64_t jbeg = seg[f_first];
+    const int64_t jend_blk = min(K, i0 + GT);
+    int my_root = active ? (int)i : 0;
+    // |d| <= eps*(min w + min h)/2 <= (w_i + h_i)/4 for eps <= 0.5; no prefilter for larger eps
+    const int reach = eps <= 0.5 ? ri.z + ri.w : (1 << 28);
+    for (int64_t j0 = jbeg; j0 < jend_blk; j0 += GT) {
+        __syncthreads();
+        const int64_t jl = j0 + threadIdx.x;
+        int4 rj = make_int4(0, 0, 0, 0);
+        if (jl < K) rj = load_xywh(cand, jl);
+        tile[threadIdx.x] = rj;
+        __syncthreads();
+        if (!active) continue;
+        const int cnt = (int)min((int64_t)GT, i - j0);   // only j < i
+        for (int q = 0; q < cnt; ++q) {
+            const int4 r2 = tile[q];
+            if (4 * abs(ri.x - r2.x) > reach || 4 * abs(ri.y - r2.y) > reach) continue;
+            const int64_t j = j0 + q;
+            if (cand[j * 5] != fi) continue;             // different frame (only at segment borders)
+            if (!similar(ri, r2, eps)) continue;
+            const int rj_root = find_root(parent, (int)j);
+            if (rj_root != my_root) my_root = unite(parent, my_root, rj_root);
+        }
     }
 }
 
