@@ -36,6 +36,7 @@ UNIT = "frames/s"
 FRAME_H, FRAME_W = 480, 640
 WINDOWS_PER_FRAME = 5061
 FLOPS_PER_WINDOW = [4969472, 19873792, 79484928]       # SURVEY.md §8a (2*MAC), stages 0/1/2
+NCU_FC1_TRAFFIC_BYTES = 5890980000 + 26478336          # dram__bytes_read.sum + dram__bytes_write.sum, m = 18944 launch
 
 
 def measured_peaks():
@@ -99,6 +100,8 @@ def cpu_port_time(n_frames_max: int, budget_s: float):
     torch.set_num_threads(cores)
     weights = synth.xavier_cascade()
     cfg = oc.Config()
+    # untimed warm-up (thread pool, allocator, lazy imports) on a small frame
+    oc.run_cascade([synth.synth_frame(96, 128, 99)], weights, oc.Config(min_window_length=0.2), dtype=torch.float32, arith="lib")
     done, t_total = 0, 0.0
     for j in range(n_frames_max):
         fr = synth.synth_frame(FRAME_H, FRAME_W, j)
@@ -227,7 +230,8 @@ def main():
     launches = eng.kernel_launches
     import ctypes as C
     fc1_ms, fc1_fl, fc1_n = C.c_double(), C.c_double(), C.c_int64()
-    L.rodc_profile_collect(C.byref(fc1_ms), C.byref(fc1_fl), C.byref(fc1_n))
+    dom_ms, dom_fl, dom_n = C.c_double(), C.c_double(), C.c_int64()
+    L.rodc_profile_collect(C.byref(fc1_ms), C.byref(fc1_fl), C.byref(fc1_n), C.byref(dom_ms), C.byref(dom_fl), C.byref(dom_n))
     L.rodc_profile_enable(0)
 
     for _ in range(2):
@@ -241,7 +245,10 @@ def main():
         e2e = frames_total / (ms_e2e / 1000.0)
         peak_tf, peak_hbm, which = measured_peaks()
         mma_per_product = 3 if args.fc1 == "tensor" else 1
-        achieved = fc1_fl.value / (fc1_ms.value / 1000.0) / 1e12 if fc1_ms.value > 0 else 0.0
+        # roofline of the dominant kernel on its dominant shape (full stage-2 chunks, K = 73728)
+        achieved = dom_fl.value / (dom_ms.value / 1000.0) / 1e12 if dom_ms.value > 0 else 0.0
+        achieved_all = fc1_fl.value / (fc1_ms.value / 1000.0) / 1e12 if fc1_ms.value > 0 else 0.0
+        dom_windows = dom_fl.value / max(dom_n.value, 1) / (2.0 * 73728 * 512)
         peak = peak_tf / 3.0
         n_boxes = int(sum(len(p) for p in last["out"]))
         d2h = int(res.boxes.shape[0]) * 6 * 4 + 8 * (len(res.stage_kept) + 1)
@@ -264,9 +271,14 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "rodc::tc::fc1_tc_kernel" if args.fc1 == "tensor" else "rodc::fc1_simt_kernel",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         # ncu --set full, same launch shape (profiles/r1b_ncu_full_fc1.txt): dram read + write
+                         "traffic": NCU_FC1_TRAFFIC_BYTES if abs(dom_windows - 18944) < 1 else None,
+                         "algorithmic_bytes": dom_windows * 73728 * 4 + 512 * 73728 * 4 + dom_windows * 512 * 4,
                          "peak_source": "%s bf16_tflops_sustained / 3 (each product = 3 fp16 MMAs)" % which,
-                         "launches": int(fc1_n.value), "avg_launch_ms": fc1_ms.value / max(int(fc1_n.value), 1),
+                         "shape": "m=%d windows x K=73728 x N=512 per launch" % int(round(dom_windows)),
+                         "launches": int(dom_n.value), "avg_launch_ms": dom_ms.value / max(int(dom_n.value), 1),
+                         "all_fc1_launches": int(fc1_n.value), "all_fc1_achieved": achieved_all,
                          "share_of_step": fc1_ms.value / ms_total if ms_total else None,
                          "mma_per_product": mma_per_product},
         }

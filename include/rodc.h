@@ -157,10 +157,13 @@ int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_
 /* ---------------------------------------------------------------- measurement hook
  * When enabled, every fc1 launch (the dominant kernel) is bracketed by cudaEvents on the stream it
  * is launched on.  rodc_profile_collect synchronises those events and returns the summed device
- * time, the algorithmic FLOPs (2*m*K*N per launch) and the launch count since the last collect.
+ * time, the algorithmic FLOPs (2*m*K*N per launch) and the launch count since the last collect --
+ * once over all fc1 launches and once over the launches of the dominant shape (largest FLOP count,
+ * i.e. full stage-2 chunks), which is what the roofline is quoted on.
  * This is the library's only process-wide state; it is off by default. */
 int rodc_profile_enable(int on);
-int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches);
+int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches,
+                         double* dom_ms, double* dom_flops, int64_t* dom_launches);
 
 #ifdef __cplusplus
 }

@@ -95,18 +95,27 @@ extern "C" int rodc_profile_enable(int on) {
     return RODC_OK;
 }
 
-extern "C" int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches) {
-    double ms = 0.0, fl = 0.0;
-    for (auto& r : g_prof) {
-        float t = 0.f;
+extern "C" int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches,
+                                    double* dom_ms, double* dom_flops, int64_t* dom_launches) {
+    double ms = 0.0, fl = 0.0, dms = 0.0, dfl = 0.0, maxfl = 0.0;
+    int64_t dn = 0;
+    std::vector<float> t(g_prof.size(), 0.f);
+    for (size_t i = 0; i < g_prof.size(); ++i) {
+        ProfRec& r = g_prof[i];
         RODC_CUDA(cudaEventSynchronize(r.b));
-        RODC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
-        ms += t; fl += r.flops;
+        RODC_CUDA(cudaEventElapsedTime(&t[i], r.a, r.b));
+        ms += t[i]; fl += r.flops;
+        if (r.flops > maxfl) maxfl = r.flops;
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
+    for (size_t i = 0; i < g_prof.size(); ++i)
+        if (g_prof[i].flops == maxfl) { dms += t[i]; dfl += g_prof[i].flops; ++dn; }
     if (fc1_ms) *fc1_ms = ms;
     if (fc1_flops) *fc1_flops = fl;
     if (fc1_launches) *fc1_launches = (int64_t)g_prof.size();
+    if (dom_ms) *dom_ms = dms;
+    if (dom_flops) *dom_flops = dfl;
+    if (dom_launches) *dom_launches = dn;
     g_prof.clear();
     return RODC_OK;
 }

@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: cf mirror, box semantics, stage-model files, app errors."""
+import os
+
+import numpy as np
+import pytest
+
+
+def test_cf_defaults_and_reset():
+    from rapidobjectdetectionusingcascadedcnns_b200 import config as cf
+    cf.reset()
+    assert cf.get("foreground_confidence_threshold") == 0.5 and cf.get("window_scale_factor") == 1.1
+    assert cf.get("min_window_length") == 0.075 and cf.get("nms") == cf.NMS_OPENCV
+    assert cf.get("nms_opencv_min_neighbors") == 1 and cf.get("max_batch_size_original") == 1200
+    assert cf.get("final_confidence_calculation") == cf.FINAL_CONFIDENCE_CALCULATION_LAST_STEP
+    cf.set("min_window_length", 0.2)
+    assert cf.get("min_window_length") == 0.2
+    cf.reset()
+    assert cf.get("min_window_length") == 0.075
+    with pytest.raises(KeyError):
+        cf.get("no_such_key")
+
+
+def test_rectangle_intersects_like_reference_test():
+    """The five pairs of the reference's `test/test_rectangles.py:9-39`."""
+    from rapidobjectdetectionusingcascadedcnns_b200.data.rectangles import Rectangle
+    pairs = [((100, 100, 200, 200), (150, 150, 175, 175)), ((150, 150, 175, 175), (100, 100, 200, 200)),
+             ((100, 100, 200, 200), (150, 150, 250, 250)), ((100, 100, 200, 200), (150, 0, 175, 250)),
+             ((100, 100, 200, 200), (50, 150, 250, 175))]
+    for a, b in pairs:
+        assert Rectangle(*a).intersects(Rectangle(*b)) and Rectangle(*b).intersects(Rectangle(*a))
+    assert not Rectangle(0, 0, 10, 10).intersects(Rectangle(11, 0, 20, 10))
+    assert Rectangle(0, 0, 9, 9).intersection_over_union(Rectangle(0, 0, 9, 9)) == 1.0
+
+
+def test_window_norm_and_vertical_enlarge():
+    from rapidobjectdetectionusingcascadedcnns_b200 import ArrayImageInfo, LabeledBoundingBox, Window
+    from rapidobjectdetectionusingcascadedcnns_b200.data.db import label
+    img = ArrayImageInfo(np.zeros((100, 120, 3), np.uint8), "a.png")
+    w = Window(4, 8, 16, 20, img, 0.23939204936916333)
+    assert (w.xmin_norm, w.ymin_norm, w.xmax_norm, w.ymax_norm) == (16, 33, 66, 83)
+    assert w.raw_norm.shape == (50, 50, 3)
+    with pytest.raises(ValueError):
+        Window(0, 0, 12, 30, img, 0.25).raw_norm
+    fg = label.get_by_iid(label.IID_FOREGROUND)
+    assert fg.is_foreground and label.get_by_iid(1) is fg
+    with pytest.raises(ValueError):
+        label.get_by_iid(7)
+    b = LabeledBoundingBox(10, 20, 40, 70, fg, 3.0, img)
+    e = LabeledBoundingBox.vertically_enlarge_bboxes([b])[0]
+    assert (e.xmin, e.ymin, e.xmax, e.ymax) == (10, 10.0, 40, 70) and e.confidence == 3.0
+    assert LabeledBoundingBox.vertically_enlarge_bboxes([LabeledBoundingBox(0, 2, 5, 30, fg)])[0].ymin == 0
+
+
+def test_stage_model_files_roundtrip(tmp_path):
+    from rapidobjectdetectionusingcascadedcnns_b200 import StageModel, synth
+    from rapidobjectdetectionusingcascadedcnns_b200.network.graph_pb import write_stage_pb
+    from rapidobjectdetectionusingcascadedcnns_b200.network.stage_model import model_paths
+    ws = synth.xavier_cascade()
+    for i, w in enumerate(ws[:2]):
+        m = StageModel(w)
+        assert (m.in_size, m.n_prev, m.bottleneck_out_width) == ([12, 24][i], 512 * i, 512 * (i + 1))
+        npz, pb = str(tmp_path / ("graph_k_%d.npz" % i)), str(tmp_path / ("graph_k_%d.pb" % i))
+        m.save(npz)
+        write_stage_pb(pb, w, stage_has_bottleneck_in=i > 0, in_size=m.in_size)
+        for path in (npz, pb):
+            r = StageModel.load(path)
+            assert all(np.array_equal(r.weights[k], m.weights[k]) for k in m.weights)
+    assert model_paths(str(tmp_path), "k", 1) == [str(tmp_path / "graph_k_1.pb"), str(tmp_path / "graph_k_1.npz")]
+    with pytest.raises(ValueError):
+        StageModel({k: v for k, v in ws[0].items() if k != "fc2_b"})
+
+
+def test_cascade_app_model_discovery_errors(tmp_path):
+    import rapidobjectdetectionusingcascadedcnns_b200 as pkg
+    pkg.cf.reset()
+    pkg.cf.set("output_graph_dir", str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        pkg.InferenceCascadeApp("missing")
+    ws = pkg.synth.xavier_cascade() if hasattr(pkg, "synth") else None
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    pkg.StageModel(synth.xavier_stage_weights(0, 12)).save(str(tmp_path / "graph_solo_0.npz"))
+    with pytest.raises(FileNotFoundError):                       # a cascade needs at least two stage files
+        pkg.InferenceCascadeApp("solo")
+    pkg.StageModel(synth.xavier_stage_weights(1, 24, n_prev_bottleneck=512)).save(str(tmp_path / "graph_solo_1.npz"))
+    app = pkg.InferenceCascadeApp("solo")
+    assert app._n_nets == 2 and app.supported_img_width == 24 and not app.last_net
+    assert app.model_full_path.endswith("graph_solo_0.pb")
+    with pytest.raises(NotImplementedError):
+        app.run_inference_on_raw_data(np.zeros((1, 12, 12, 3), np.uint8))
+    single = pkg.InferenceApp("nope")
+    with pytest.raises(FileNotFoundError):
+        single._stage_files()
+    pkg.cf.reset()
