@@ -441,6 +441,214 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
     }
 }
 
+// ------------------------------------------------------------------ feature kernel v3 (streaming, barrier free)
+// Same arithmetic as v2, but the conv output never touches shared memory: warp (cg, part) owns 16
+// channels x one quarter of the window rows and streams down its rows.  M row r of an MMA tile maps to
+// pixel 16j + 2 (r % 8) + r / 8, so every thread holds two horizontally adjacent pixels and the
+// horizontal 3-max needs just two lane shuffles per value; the vertical 3-max is a sliding window of
+// three row registers.  The two n-tiles of a warp use permuted weight columns so that thread t owns
+// channels 4t..4t+3 of its group: stores are 8-byte, four lanes fill one 32-byte sector.  One
+// __syncthreads per window (input staging is double buffered).  This is also the producer the fused
+// feature->fc1 kernel needs (round 2): only the final store changes.
+template <int OUT_SPLIT, int S>
+__global__ void __launch_bounds__(FEAT_THREADS, 2)
+features_stream_kernel(SrcDev src, int64_t first, int64_t n,
+                       const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
+                       float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NQ = 4, RQ = S / NQ;
+    constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* inh0 = reinterpret_cast<__half*>(smem_raw);
+    int* tabs = reinterpret_cast<int*>(smem_raw + (size_t)2 * INH * 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int cg = warp & 1, part = warp >> 1;
+    const int ya = part * RQ, yb = ya + RQ;
+
+    // B fragments of this warp's two n-tiles (permuted columns, see stage.cu) and its 4 biases
+    uint32_t bf[3][2][2][2];
+    #pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+        #pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(conv_frag) + (((ky * 4 + (cg * 2 + sub)) * 2 + h) * 32 + lane));
+                bf[ky][sub][h][0] = v.x; bf[ky][sub][h][1] = v.y;
+            }
+    float bias4[4];
+    #pragma unroll
+    for (int c = 0; c < 4; ++c) bias4[c] = __ldg(conv_b + 16 * cg + 4 * t + c);
+
+    int iter = 0;
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x, ++iter) {
+        const int64_t w = first + wrel;
+        __half* inh = inh0 + (size_t)(iter & 1) * INH;
+        // ---- stage the window as zero-padded fp16 [P][P][4]
+        {
+            uint4* z = reinterpret_cast<uint4*>(inh);
+            for (int i = tid; i < INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        Crop crop;
+        if (src.kind == RODC_SRC_RECROP) {
+            crop = make_crop(src, w);
+            fill_recrop_tables(crop, S, tabs);                 // safe: everyone left the previous window's staging
+        }
+        __syncthreads();                                       // zero fill (and tables) visible
+        if (src.kind == RODC_SRC_RECROP) {
+            for (int i = tid; i < S * S; i += FEAT_THREADS) {
+                const int y = i / S, x = i - y * S;
+                int px[3];
+                recrop_pixel(crop, S, tabs, y, x, px);
+                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
+                d[0] = __halves2half2(__int2half_rn(px[0]), __int2half_rn(px[1]));
+                d[1] = __halves2half2(__int2half_rn(px[2]), __int2half_rn(0));
+            }
+        } else {
+            const uint8_t* p; int pitch;
+            if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+            else {
+                const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
+                const int32_t* wr = src.win + j * 8;
+                const LevelInfo& lv = src.levels[wr[0]];
+                p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+                pitch = lv.w * 3;
+            }
+            for (int i = tid; i < S * S; i += FEAT_THREADS) {
+                const int y = i / S, x = i - y * S;
+                const uint8_t* q = p + (int64_t)y * pitch + x * 3;
+                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
+                d[0] = __halves2half2(__int2half_rn((int)q[0]), __int2half_rn((int)q[1]));
+                d[1] = __halves2half2(__int2half_rn((int)q[2]), __int2half_rn(0));
+            }
+        }
+        __syncthreads();                                       // window staged
+
+        float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C;
+        __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C : nullptr;
+        __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C : nullptr;
+
+        // sliding window of horizontal maxima: [tile][pixel 0/1][4 channels]
+        float hA[TR][2][4], hB[TR][2][4];                      // max(h[y-2], h[y-1]) and h[y-1]
+        #pragma unroll
+        for (int j = 0; j < TR; ++j)
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) { hA[j][q][c] = 0.f; hB[j][q][c] = 0.f; }
+
+        #pragma unroll 1
+        for (int yy = ya - 1; yy <= yb; ++yy) {
+            float v[TR][2][4];
+            const bool row_in = yy >= 0 && yy < S;
+            if (row_in) {
+                #pragma unroll
+                for (int j = 0; j < TR; ++j) {
+                    // A rows: pixel x0 = 16 j + 2 g (fragment row g) and x0 + 1 (row g + 8)
+                    const int x0 = 16 * j + 2 * g;
+                    const int xc = x0 < S ? x0 : 0;             // masked tiles read pixel 0 (finite), zeroed below
+                    const uint32_t* base = reinterpret_cast<const uint32_t*>(inh + ((yy * P) + xc) * 4) + t;
+                    float acc[2][4];
+                    #pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) { acc[sub][0] = acc[sub][1] = acc[sub][2] = acc[sub][3] = 0.f; }
+                    #pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t a0 = base[ky * P * 2], a1 = base[ky * P * 2 + 2];
+                        const uint32_t a2 = base[ky * P * 2 + 4], a3 = base[ky * P * 2 + 6];
+                        #pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            mma16816(acc[sub], a0, a1, a2, a3, bf[ky][sub][1][0], bf[ky][sub][1][1]);   // lo weights first
+                            mma16816(acc[sub], a0, a1, a2, a3, bf[ky][sub][0][0], bf[ky][sub][0][1]);
+                        }
+                    }
+                    const bool in0 = x0 < S, in1 = x0 + 1 < S;
+                    #pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        v[j][0][2 * sub + 0] = in0 ? fmaxf(fmaf(acc[sub][0], conv_scale, bias4[2 * sub + 0]), 0.f) : 0.f;
+                        v[j][0][2 * sub + 1] = in0 ? fmaxf(fmaf(acc[sub][1], conv_scale, bias4[2 * sub + 1]), 0.f) : 0.f;
+                        v[j][1][2 * sub + 0] = in1 ? fmaxf(fmaf(acc[sub][2], conv_scale, bias4[2 * sub + 0]), 0.f) : 0.f;
+                        v[j][1][2 * sub + 1] = in1 ? fmaxf(fmaf(acc[sub][3], conv_scale, bias4[2 * sub + 1]), 0.f) : 0.f;
+                    }
+                }
+            }
+            // horizontal 3-max (zero outside the window == SAME padding for post-ReLU data)
+            float hc[TR][2][4];
+            if (row_in) {
+                float R[TR][4], L[TR][4];
+                #pragma unroll
+                for (int j = 0; j < TR; ++j)
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        R[j][c] = __shfl_sync(0xffffffffu, v[j][0][c], (lane + 4) & 31);    // first pixel of lane g+1 (wraps to g=0)
+                        L[j][c] = __shfl_sync(0xffffffffu, v[j][1][c], (lane + 28) & 31);   // second pixel of lane g-1 (wraps to g=7)
+                    }
+                #pragma unroll
+                for (int j = 0; j < TR; ++j)
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float rn = (g < 7) ? R[j][c] : (j + 1 < TR ? R[(j + 1 < TR) ? j + 1 : j][c] : 0.f);
+                        const float ln = (g > 0) ? L[j][c] : (j > 0 ? L[(j > 0) ? j - 1 : j][c] : 0.f);
+                        hc[j][0][c] = fmaxf(fmaxf(ln, v[j][0][c]), v[j][1][c]);
+                        hc[j][1][c] = fmaxf(fmaxf(v[j][0][c], v[j][1][c]), rn);
+                    }
+            } else {
+                #pragma unroll
+                for (int j = 0; j < TR; ++j)
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        #pragma unroll
+                        for (int c = 0; c < 4; ++c) hc[j][q][c] = 0.f;
+            }
+            // vertical: pooled row yy-1 = max(h[yy-2], h[yy-1], h[yy])
+            const int yo = yy - 1;
+            if (yo >= ya && yo < yb) {
+                #pragma unroll
+                for (int j = 0; j < TR; ++j)
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int x = 16 * j + 2 * g + q;
+                        if (x < S) {
+                            float m[4];
+                            #pragma unroll
+                            for (int c = 0; c < 4; ++c) m[c] = fmaxf(hA[j][q][c], hc[j][q][c]);
+                            const int64_t k = ((int64_t)yo * S + x) * C + 16 * cg + 4 * t;
+                            if (OUT_SPLIT) {
+                                const float s0 = m[0] * a_scale, s1 = m[1] * a_scale, s2 = m[2] * a_scale, s3 = m[3] * a_scale;
+                                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                                uint2 uh, ul;
+                                uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                                ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(oh + k) = uh;
+                                *reinterpret_cast<uint2*>(ol + k) = ul;
+                            } else {
+                                *reinterpret_cast<float4*>(of + k) = make_float4(m[0], m[1], m[2], m[3]);
+                            }
+                        }
+                    }
+            }
+            #pragma unroll
+            for (int j = 0; j < TR; ++j)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        hA[j][q][c] = fmaxf(hB[j][q][c], hc[j][q][c]);
+                        hB[j][q][c] = hc[j][q][c];
+                    }
+        }
+    }
+}
+
+template <int S>
+static size_t feat3_smem_bytes() {
+    constexpr int P = S + 2;
+    constexpr int INH = (P * P * 4 + 64 + 7) & ~7;
+    return (size_t)2 * INH * 2 + (size_t)6 * S * 4;
+}
+
 static size_t feat2_smem_bytes(int S, int R) {
     const int P = S + 2;
     const size_t inh = (size_t)((P * P * 4 + 16 + 7) & ~7) * 2;
@@ -521,6 +729,22 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
     const float conv_scale = ldexpf(1.f, -s->c_exp);
     // persistent-style grid: two CTAs per SM, each loops over windows
     const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
+    static int use_v2 = -1;
+    if (use_v2 < 0) { const char* e = getenv("RODC_FEATURES_V2"); use_v2 = (e && e[0] == '1') ? 1 : 0; }
+    if (!use_v2 && (S == 12 || S == 24 || S == 48)) {
+#define RODC_LAUNCH_FEAT3(SPLIT, ST_)                                                                                      \
+        do {                                                                                                              \
+            const size_t smem = feat3_smem_bytes<ST_>();                                                                  \
+            RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->conv_frag_perm, s->conv_b,  \
+                                                                                 conv_scale, a_scale, out_f32, out_hi, out_lo); \
+        } while (0)
+        if (out_f32) { if (S == 12) RODC_LAUNCH_FEAT3(0, 12); else if (S == 24) RODC_LAUNCH_FEAT3(0, 24); else RODC_LAUNCH_FEAT3(0, 48); }
+        else { if (S == 12) RODC_LAUNCH_FEAT3(1, 12); else if (S == 24) RODC_LAUNCH_FEAT3(1, 24); else RODC_LAUNCH_FEAT3(1, 48); }
+#undef RODC_LAUNCH_FEAT3
+        RODC_LAUNCH_CHECK();
+        return RODC_OK;
+    }
 #define RODC_LAUNCH_FEAT(SPLIT, ST_, RT_, Rv)                                                                              \
     do {                                                                                                                  \
         const size_t smem = feat2_smem_bytes(S, Rv);                                                                      \

@@ -13,6 +13,7 @@ rodc_stage::~rodc_stage() {
     if (fc1_hi) cudaFree(fc1_hi);
     if (fc1_lo) cudaFree(fc1_lo);
     if (conv_frag) cudaFree(conv_frag);
+    if (conv_frag_perm) cudaFree(conv_frag_perm);
 }
 
 namespace rodc {
@@ -158,7 +159,7 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
         for (size_t i = 0; i < nconv; ++i) { double a = fabs((double)conv_w[i]); if (a > cmax) cmax = a; }
         s->c_exp = pow2_headroom(cmax, 16384.0);
         const float cs = ldexpf(1.f, s->c_exp);
-        std::vector<uint32_t> frag((size_t)3 * 4 * 2 * 32 * 2, 0u);
+        std::vector<uint32_t> frag((size_t)3 * 4 * 2 * 32 * 2, 0u), fragp(frag.size(), 0u);
         auto wval = [&](int ky, int j, int nn) -> float {
             const int kx = j >> 2, ci = j & 3;
             if (kx > 2 || ci > 2) return 0.f;
@@ -180,10 +181,19 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
                             const int j0 = 2 * tt + 8 * r;
                             const uint32_t lo16 = halfbits(wval(ky, j0, nn), h), hi16 = halfbits(wval(ky, j0 + 1, nn), h);
                             frag[((((size_t)(ky * 4 + nt) * 2 + h) * 32) + lane) * 2 + r] = lo16 | (hi16 << 16);
+                            // permuted variant (features v3): n-tile nt = 2*cg + sub, column gg -> channel
+                            // 16*cg + 4*(gg/2) + 2*sub + gg%2, so lane t owns channels 4t..4t+3 of its group
+                            const int np = 16 * (nt >> 1) + 4 * (gg >> 1) + 2 * (nt & 1) + (gg & 1);
+                            const uint32_t plo = halfbits(wval(ky, j0, np), h), phi = halfbits(wval(ky, j0 + 1, np), h);
+                            fragp[((((size_t)(ky * 4 + nt) * 2 + h) * 32) + lane) * 2 + r] = plo | (phi << 16);
                         }
                     }
         if (cudaMalloc(&s->conv_frag, frag.size() * 4) != cudaSuccess ||
             cudaMemcpy(s->conv_frag, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("upload of the conv fragments failed"); delete s; return RODC_ERR_NOMEM;
+        }
+        if (cudaMalloc(&s->conv_frag_perm, fragp.size() * 4) != cudaSuccess ||
+            cudaMemcpy(s->conv_frag_perm, fragp.data(), fragp.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
             set_error("upload of the conv fragments failed"); delete s; return RODC_ERR_NOMEM;
         }
     }

@@ -20,6 +20,7 @@ struct rodc_stage {
     __half* fc1_hi = nullptr;
     __half* fc1_lo = nullptr;
     uint32_t* conv_frag = nullptr;  // mma.sync B fragments of the conv: [3 ky][4 nt][hi,lo][32 lanes][2] half2
+    uint32_t* conv_frag_perm = nullptr;   // same, n-tile columns permuted so a thread owns 4 adjacent channels (v3)
     int c_exp = 0;              // conv weights are scaled by 2^c_exp before the fp16 split
     int a_exp = 0;              // features are scaled by 2^a_exp before the fp16 split
     int w_exp = 0;              // weights  are scaled by 2^w_exp before the fp16 split
