@@ -62,6 +62,14 @@ def _defaults():
     cf["log_window_extraction_details"] = False            # :473
     cf["log_cascade_confidence_details"] = False           # :476
     cf["output_graph_dir"] = os.environ.get("RODC_GRAPH_DIR", os.path.join(os.getcwd(), "output", "graph"))   # :523
+    # FDDB evaluation caller (`config.py:479,552-558`); the external Perl / gnuplot scoring is out of scope
+    cf["foreground_equals_face"] = True
+    _root = os.environ.get("RODC_DATA_ROOT", os.path.join(os.getcwd(), "input"))
+    cf["fddb_root_dir"] = os.path.join(_root, "fddb")
+    cf["fddb_folds_dir"] = os.path.join(cf["fddb_root_dir"], "FDDB-folds")
+    cf["fddb_img_base_dir"] = os.path.join(cf["fddb_root_dir"], "images/original/foreground")
+    cf["fddb_detection_output_dir"] = os.path.join(os.getcwd(), "output", "fddb_detection_output")
+    cf["session_key"] = "session"
     # librodc
     cf["fc1_impl"] = FC1_IMPL_TENSOR
     cf["max_windows_per_launch"] = 1 << 18                 # frame batches are cut so stage 0 stays below this

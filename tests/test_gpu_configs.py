@@ -6,6 +6,8 @@ config 5  3840x2160, 161 969 windows, > 99.9 % stage-1 rejection -> size-indepen
 config 1  single 48-px net on 640x480 (3 319 windows)                                       -> oracle compare
 Offsets on fc2.b[1] are the documented calibration knob; the same offsets feed both sides.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -165,3 +167,36 @@ def test_config1_single_net_640x480(pkg):
         res = app._engine.run_frames(frame[None], keep_trace=True)
         diff = np.setxor1d(res.trace["keep"][0].cpu().numpy(), r.stages[0].keep_idx)
         assert diff.size and np.abs(r.stages[0].logits[diff, 1] - r.stages[0].logits[diff, 0]).max() < EPS[2]
+
+
+def test_fddb_caller_dense_pyramid(pkg, tmp_path):
+    """SURVEY.md §8f #2: the FDDB caller's regime (factor 1.005, merge=False, vertical enlarge) and writer."""
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    from rapidobjectdetectionusingcascadedcnns_b200.app.evaluate_fddb_app import EvaluateFDDBApp
+    ocfg = oc.Config(window_scale_factor=1.005, vertically_enlarge_bboxes=True)
+    offsets = _calibrate([0.02, 0.3, 0.5], oc.Config())
+    weights = _weights(offsets)
+    pkg.cf.set("fddb_detection_output_dir", str(tmp_path))
+    pkg.cf.set("fddb_img_base_dir", "/fddb/img")
+    frames = [synth.synth_frame(*synth.fddb_shape(0), 100), synth.synth_frame(180, 200, 101)]
+    infos = [pkg.ArrayImageInfo(frames[0], "/fddb/img/2002/08/11/big/img_591.jpg"),
+             pkg.ArrayImageInfo(frames[1], "/fddb/img/2002/08/26/big/img_265.jpg")]
+    app = pkg.InferenceCascadeApp("fddb", stage_models=[pkg.StageModel(w) for w in weights])
+    ev = EvaluateFDDBApp("t", inference_app=app, folds=[infos[:1], infos[1:]])
+    assert pkg.cf.get("window_scale_factor") == 1.005 and pkg.cf.get("inference_merge") is False
+    plan = app._engine.plan_for(450, 400)
+    assert (plan.n_levels, plan.n_windows) == (496, 116065)                 # SURVEY.md App. C.1
+    # the small frame against the fp64 oracle (vertically enlarged float boxes)
+    got = _rows(ev.results[2])[0]
+    r64 = oc.run_cascade([frames[1]], weights, ocfg, dtype=torch.float64, arith="lib")
+    ref = np.column_stack([r64.boxes, r64.conf]).astype(np.float64).reshape(-1, 5)
+    if got.shape == ref.shape:
+        np.testing.assert_allclose(got, ref)
+    else:
+        _compare_frame(pkg, app._engine, frames[1], weights, oc.Config(window_scale_factor=1.005), got[:0])
+    text = open(os.path.join(ev.export_dir, "fold-01-out.txt")).read().split("\n")
+    assert text[0] == "2002/08/11/big/img_591" and int(text[1]) == len(ev.results[1][0])
+    if ev.results[1][0]:
+        b = ev.results[1][0][0]
+        assert text[2] == "{} {} {} {} {}".format(b.xmin, b.ymin, b.width, b.height, b.confidence)
