@@ -100,14 +100,14 @@ class InferenceApp(AbstractInferenceApp):
         fg = label.get_by_iid(label.IID_FOREGROUND)
         post_nms = cf.get("nms") == cf.NMS_OPENCV
         out = [[] for _ in range(n_frames)]
-        for k in range(res.boxes.shape[0]):
-            f = int(res.frame[k])
-            b = res.boxes[k]
-            if post_nms:      # numpy ints and float(weight) like `:203-212`
-                box = LabeledBoundingBox(b[0], b[1], b[2], b[3], fg, float(res.conf[k]), infos[f])
-            else:             # python ints and the float32 softmax like cascade `:319-334`
-                box = LabeledBoundingBox(int(b[0]), int(b[1]), int(b[2]), int(b[3]), fg, res.conf[k], infos[f])
-            out[f].append(box)
+        frames = res.frame.tolist()
+        if post_nms:          # numpy ints and float(weight) like `:203-212`
+            for f, b, c in zip(frames, res.boxes, res.conf.tolist()):
+                x0, y0, x1, y1 = b
+                out[f].append(LabeledBoundingBox(x0, y0, x1, y1, fg, c, infos[f]))
+        else:                 # python ints and the float32 softmax like cascade `:319-334`
+            for f, b, c in zip(frames, res.boxes.tolist(), res.conf):
+                out[f].append(LabeledBoundingBox(b[0], b[1], b[2], b[3], fg, c, infos[f]))
         if cf.get("vertically_enlarge_bboxes"):
             out = [LabeledBoundingBox.vertically_enlarge_bboxes(bs) if bs else bs for bs in out]
         return out

@@ -129,6 +129,52 @@ __global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restri
     }
 }
 
+// Per-frame variant for the common case (a frame's candidates fit in shared memory): one CTA per
+// frame keeps the rectangles AND the union-find forest in smem, so the pair scan reads broadcast
+// LDS.128 and every find / CAS is a ~30-cycle shared-memory operation instead of a contended global
+// atomic.  The forest is written back with global indices for group_finalize_kernel.
+constexpr int GS_THREADS = 1024;
+__global__ void __launch_bounds__(GS_THREADS) group_union_smem_kernel(const int32_t* __restrict__ cand,
+                                                                      const int32_t* __restrict__ seg,
+                                                                      int32_t* __restrict__ parent, double eps, int cap) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int f = blockIdx.x;
+    const int s0 = seg[f], n = seg[f + 1] - s0;
+    if (n <= 0) return;
+    // a frame that exceeds the caller's bound falls back to global memory (same algorithm, local indices)
+    const bool in_smem = n <= cap;
+    int4* rect = reinterpret_cast<int4*>(gsm);
+    int32_t* par = in_smem ? reinterpret_cast<int32_t*>(rect + cap) : parent + s0;
+    for (int i = threadIdx.x; i < n; i += GS_THREADS) { if (in_smem) rect[i] = load_xywh(cand, s0 + i); par[i] = i; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += GS_THREADS) {
+        const int4 ri = in_smem ? rect[i] : load_xywh(cand, s0 + i);
+        const int reach = eps <= 0.5 ? ri.z + ri.w : (1 << 28);
+        int my_root = i;
+        for (int j = 0; j < i; ++j) {
+            const int4 r2 = in_smem ? rect[j] : load_xywh(cand, s0 + j);
+            if (4 * abs(ri.x - r2.x) > reach || 4 * abs(ri.y - r2.y) > reach) continue;
+            if (!similar(ri, r2, eps)) continue;
+            const int rj = find_root(par, j);
+            if (rj != my_root) my_root = unite(par, my_root, rj);
+        }
+    }
+    __syncthreads();
+    // flatten, then switch to global indices for group_finalize_kernel
+    int roots[8];
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n && cnt < 8; i += GS_THREADS) roots[cnt++] = find_root(par, i);
+    if (n <= 8 * GS_THREADS) {
+        __syncthreads();
+        cnt = 0;
+        for (int i = threadIdx.x; i < n; i += GS_THREADS) parent[s0 + i] = s0 + roots[cnt++];
+    } else {                                              // very large frames: flatten in place first
+        for (int i = threadIdx.x; i < n; i += GS_THREADS) { const int r = find_root(par, i); par[i] = r; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += GS_THREADS) { const int r = par[i]; __syncwarp(); parent[s0 + i] = s0 + r; }
+    }
+}
+
 // one block per frame: class numbering (order of first member = order of roots), sums, means,
 // filters, ordered per-frame output into tmp.
 __global__ void __launch_bounds__(1024) group_finalize_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ seg,
@@ -293,7 +339,8 @@ extern "C" int64_t rodc_group_scratch_bytes(int64_t k, int n_frames) {
     return align16((F + 1) * 4) * 2 + align16(F * 4) * 2 + align16(K * 4) * 2 + align16(K * 20) + align16(K * 16) + align16(K * 24) + 256;
 }
 
-extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
+extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int64_t max_per_frame,
+                                     int min_neighbors, double eps,
                                      int32_t* out, int64_t* out_count, void* scratch, void* stream) {
     RODC_CHECK_ARG(out_count != nullptr, "rodc_group_rectangles: out_count is NULL");
     RODC_CHECK_ARG(k >= 0 && k < (1ll << 30), "rodc_group_rectangles: bad k");
@@ -311,7 +358,17 @@ extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frame
     RODC_LAUNCH_CHECK();
     group_init_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(g.parent, g.sums, k);
     RODC_LAUNCH_CHECK();
-    group_union_kernel<<<blocks, 256, 0, st>>>(cand, k, g.seg, g.parent, eps);
+    // frames whose candidates fit in shared memory (20 B each) take the per-frame smem kernel; the caller's
+    // bound on candidates per frame (e.g. the plan's window count) avoids a host sync to size the launch
+    const int64_t smem_cap = 200 * 1024 / 20;
+    const int64_t per_frame = (max_per_frame > 0 && max_per_frame < k) ? max_per_frame : k;
+    if (per_frame <= smem_cap) {
+        const size_t smem = (size_t)per_frame * 20 + 16;
+        RODC_CUDA(cudaFuncSetAttribute(group_union_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_union_smem_kernel<<<n_frames, GS_THREADS, smem, st>>>(cand, g.seg, g.parent, eps, (int)per_frame);
+    } else {
+        group_union_kernel<<<blocks, 256, 0, st>>>(cand, k, g.seg, g.parent, eps);
+    }
     RODC_LAUNCH_CHECK();
     group_finalize_kernel<<<n_frames, 1024, 0, st>>>(cand, g.seg, g.parent, g.cls, g.sums, g.rrect, g.tmp, g.fcount, min_neighbors, eps);
     RODC_LAUNCH_CHECK();

@@ -289,3 +289,27 @@ def test_group_rectangles_multi_frame_random(nat, thr):
 def test_group_rectangles_empty(nat):
     out, count = nat.group_rectangles(torch.zeros((0, 5), dtype=torch.int32, device="cuda"), 0, 3, 1)
     assert int(count.item()) == 0
+
+
+def test_group_rectangles_all_code_paths_agree(nat):
+    """smem per-frame kernel, its in-kernel global fallback (bound too small) and the tiled global kernel
+    (k beyond the smem cap) must give the same answer as the oracle."""
+    rs = np.random.RandomState(5)
+    rows = []
+    n_frames = 40
+    for f in range(n_frames):
+        k = int(rs.randint(200, 420))
+        base = rs.randint(0, 400, (int(rs.randint(2, 12)), 2))
+        for _ in range(k):
+            b = base[rs.randint(len(base))]
+            s = int(rs.randint(12, 100))
+            x, y = int(b[0] + rs.randint(-9, 10)), int(b[1] + rs.randint(-9, 10))
+            rows.append([f, x, y, x + s + int(rs.randint(-3, 4)), y + s + int(rs.randint(-3, 4))])
+    cand = np.asarray(rows, np.int32)
+    assert len(cand) > 10240                                   # > smem cap when no per-frame bound is given
+    ref = _group_ref(cand, n_frames, 1)
+    d = dev(cand)
+    for bound in (0, 420, 64):                                 # global tiled / smem / smem with too-small bound
+        out, count = nat.group_rectangles(d, len(cand), n_frames, 1, max_per_frame=bound)
+        c = int(count.item())
+        assert np.array_equal(out.cpu().numpy()[:c], ref), bound
