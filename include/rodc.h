@@ -149,12 +149,9 @@ int rodc_compact(const float* probs, int64_t n, double threshold,
  * float32 mean + cvRound, size filter, nested filter; classes in order of first member.
  *   cand [K,5] i32 (frame_id, xmin,ymin,xmax,ymax), grouped by ascending frame id
  *   out  [K,6] i32 (frame_id, x, y, w, h, weight), frames ascending, class order inside
- *   out_count: device int64.  scratch: rodc_group_scratch_bytes(K, n_frames).
- *   max_per_frame: upper bound of candidates in one frame (0 = unknown); when it fits in shared
- *   memory the per-frame union-find runs there instead of in global memory. */
+ *   out_count: device int64.  scratch: rodc_group_scratch_bytes(K, n_frames). */
 int64_t rodc_group_scratch_bytes(int64_t k, int n_frames);
-int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int64_t max_per_frame,
-                          int min_neighbors, double eps,
+int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
                           int32_t* out, int64_t* out_count, void* scratch, void* stream);
 
 /* ---------------------------------------------------------------- measurement hook

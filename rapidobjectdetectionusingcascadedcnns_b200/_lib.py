@@ -59,7 +59,7 @@ SIGNATURES = {
     "rodc_group_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int]),
     "rodc_profile_enable": (C.c_int, [C.c_int]),
     "rodc_profile_collect": (C.c_int, [c_f64p, c_f64p, c_i64p, c_f64p, c_f64p, c_i64p]),
-    "rodc_group_rectangles": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_double, vp, vp, vp, vp]),
+    "rodc_group_rectangles": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp]),
 }
 
 

@@ -86,92 +86,50 @@ __device__ __forceinline__ int4 load_xywh(const int32_t* cand, int64_t i) {
     return make_int4(c[1], c[2], c[3] - c[1], c[4] - c[2]);       // (x, y, w, h) as _run_nms builds them
 }
 
-// Pair scan, tiled through shared memory.  grid.x = tiles of 256 candidates (global index space);
-// each thread owns candidate i and tests every j < i of the same frame, 256 at a time from smem.
-// An integer prefilter (a superset of the exact predicate for eps <= 0.5) rejects most pairs before
-// the double-precision SimilarRects test; the thread keeps its current root in a register so that
-// already-merged neighbours cost one find and no atomic.
+// Pair scan over a 2-D triangle of 256 x 256 tiles of the (frame-sorted) candidate index space:
+// block (bi, bj <= bi) tests candidates i of tile bi against candidates j < i of tile bj staged in
+// shared memory.  Tiles that cannot share a frame exit at once, so the grid is sized from K alone
+// (no host sync) while the K^2/2 predicate evaluations spread evenly over all SMs.  An integer
+// prefilter (a superset of the exact predicate for eps <= 0.5) rejects most pairs before the
+// double-precision SimilarRects test; unions are rare and go to the global forest with atomicCAS.
+// (A one-CTA-per-frame variant with the forest in shared memory was measured 10x slower: the scan,
+// not the atomics, is the cost, and it needs all SMs.)
 constexpr int GT = 256;
 __global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restrict__ cand, int64_t K,
                                                          const int32_t* __restrict__ seg, int32_t* __restrict__ parent, double eps) {
     __shared__ int4 tile[GT];
-    const int64_t i0 = (int64_t)blockIdx.x * GT;
-    const int64_t i = i0 + threadIdx.x;
-    const bool active = i < K;
-    int4 ri = make_int4(0, 0, 0, 0);
-    int fi = -1;
-    if (active) { ri = load_xywh(cand, i); fi = cand[i * 5]; }
-    // candidates are grouped by frame: this block needs j from the first frame's segment start on
+    __shared__ int tframe[GT];
+    // linear block id -> (bi, bj) with bj <= bi
+    const long long b = blockIdx.x;
+    long long bi = (long long)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > b) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    const long long bj = b - bi * (bi + 1) / 2;
+    const int64_t i0 = bi * GT, j0 = bj * GT;
+    // the i tile's first frame starts at seg[f_first]; j tiles that end before it hold other frames only
     const int f_first = cand[i0 * 5];
-    const int64_t jbeg = seg[f_first];
-    const int64_t jend_blk = min(K, i0 + GT);
-    int my_root = active ? (int)i : 0;
+    if (j0 + GT <= seg[f_first]) return;
+    const int64_t jl = j0 + threadIdx.x;
+    int4 rj = make_int4(0, 0, 0, 0);
+    int fj = -2;
+    if (jl < K) { rj = load_xywh(cand, jl); fj = cand[jl * 5]; }
+    tile[threadIdx.x] = rj; tframe[threadIdx.x] = fj;
+    __syncthreads();
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= K) return;
+    const int4 ri = load_xywh(cand, i);
+    const int fi = cand[i * 5];
     // |d| <= eps*(min w + min h)/2 <= (w_i + h_i)/4 for eps <= 0.5; no prefilter for larger eps
     const int reach = eps <= 0.5 ? ri.z + ri.w : (1 << 28);
-    for (int64_t j0 = jbeg; j0 < jend_blk; j0 += GT) {
-        __syncthreads();
-        const int64_t jl = j0 + threadIdx.x;
-        int4 rj = make_int4(0, 0, 0, 0);
-        if (jl < K) rj = load_xywh(cand, jl);
-        tile[threadIdx.x] = rj;
-        __syncthreads();
-        if (!active) continue;
-        const int cnt = (int)min((int64_t)GT, i - j0);   // only j < i
-        for (int q = 0; q < cnt; ++q) {
-            const int4 r2 = tile[q];
-            if (4 * abs(ri.x - r2.x) > reach || 4 * abs(ri.y - r2.y) > reach) continue;
-            const int64_t j = j0 + q;
-            if (cand[j * 5] != fi) continue;             // different frame (only at segment borders)
-            if (!similar(ri, r2, eps)) continue;
-            const int rj_root = find_root(parent, (int)j);
-            if (rj_root != my_root) my_root = unite(parent, my_root, rj_root);
-        }
-    }
-}
-
-// Per-frame variant for the common case (a frame's candidates fit in shared memory): one CTA per
-// frame keeps the rectangles AND the union-find forest in smem, so the pair scan reads broadcast
-// LDS.128 and every find / CAS is a ~30-cycle shared-memory operation instead of a contended global
-// atomic.  The forest is written back with global indices for group_finalize_kernel.
-constexpr int GS_THREADS = 1024;
-__global__ void __launch_bounds__(GS_THREADS) group_union_smem_kernel(const int32_t* __restrict__ cand,
-                                                                      const int32_t* __restrict__ seg,
-                                                                      int32_t* __restrict__ parent, double eps, int cap) {
-    extern __shared__ __align__(16) unsigned char gsm[];
-    const int f = blockIdx.x;
-    const int s0 = seg[f], n = seg[f + 1] - s0;
-    if (n <= 0) return;
-    // a frame that exceeds the caller's bound falls back to global memory (same algorithm, local indices)
-    const bool in_smem = n <= cap;
-    int4* rect = reinterpret_cast<int4*>(gsm);
-    int32_t* par = in_smem ? reinterpret_cast<int32_t*>(rect + cap) : parent + s0;
-    for (int i = threadIdx.x; i < n; i += GS_THREADS) { if (in_smem) rect[i] = load_xywh(cand, s0 + i); par[i] = i; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += GS_THREADS) {
-        const int4 ri = in_smem ? rect[i] : load_xywh(cand, s0 + i);
-        const int reach = eps <= 0.5 ? ri.z + ri.w : (1 << 28);
-        int my_root = i;
-        for (int j = 0; j < i; ++j) {
-            const int4 r2 = in_smem ? rect[j] : load_xywh(cand, s0 + j);
-            if (4 * abs(ri.x - r2.x) > reach || 4 * abs(ri.y - r2.y) > reach) continue;
-            if (!similar(ri, r2, eps)) continue;
-            const int rj = find_root(par, j);
-            if (rj != my_root) my_root = unite(par, my_root, rj);
-        }
-    }
-    __syncthreads();
-    // flatten, then switch to global indices for group_finalize_kernel
-    int roots[8];
-    int cnt = 0;
-    for (int i = threadIdx.x; i < n && cnt < 8; i += GS_THREADS) roots[cnt++] = find_root(par, i);
-    if (n <= 8 * GS_THREADS) {
-        __syncthreads();
-        cnt = 0;
-        for (int i = threadIdx.x; i < n; i += GS_THREADS) parent[s0 + i] = s0 + roots[cnt++];
-    } else {                                              // very large frames: flatten in place first
-        for (int i = threadIdx.x; i < n; i += GS_THREADS) { const int r = find_root(par, i); par[i] = r; }
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += GS_THREADS) { const int r = par[i]; __syncwarp(); parent[s0 + i] = s0 + r; }
+    const int cnt = (int)min((int64_t)GT, i - j0);           // only j < i
+    int my_root = (int)i;
+    for (int q = 0; q < cnt; ++q) {
+        const int4 r2 = tile[q];
+        if (4 * abs(ri.x - r2.x) > reach || 4 * abs(ri.y - r2.y) > reach) continue;
+        if (tframe[q] != fi) continue;
+        if (!similar(ri, r2, eps)) continue;
+        const int rjr = find_root(parent, (int)(j0 + q));
+        if (rjr != my_root) my_root = unite(parent, my_root, rjr);
     }
 }
 
@@ -339,8 +297,7 @@ extern "C" int64_t rodc_group_scratch_bytes(int64_t k, int n_frames) {
     return align16((F + 1) * 4) * 2 + align16(F * 4) * 2 + align16(K * 4) * 2 + align16(K * 20) + align16(K * 16) + align16(K * 24) + 256;
 }
 
-extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int64_t max_per_frame,
-                                     int min_neighbors, double eps,
+extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
                                      int32_t* out, int64_t* out_count, void* scratch, void* stream) {
     RODC_CHECK_ARG(out_count != nullptr, "rodc_group_rectangles: out_count is NULL");
     RODC_CHECK_ARG(k >= 0 && k < (1ll << 30), "rodc_group_rectangles: bad k");
@@ -358,16 +315,11 @@ extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frame
     RODC_LAUNCH_CHECK();
     group_init_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(g.parent, g.sums, k);
     RODC_LAUNCH_CHECK();
-    // frames whose candidates fit in shared memory (20 B each) take the per-frame smem kernel; the caller's
-    // bound on candidates per frame (e.g. the plan's window count) avoids a host sync to size the launch
-    const int64_t smem_cap = 200 * 1024 / 20;
-    const int64_t per_frame = (max_per_frame > 0 && max_per_frame < k) ? max_per_frame : k;
-    if (per_frame <= smem_cap) {
-        const size_t smem = (size_t)per_frame * 20 + 16;
-        RODC_CUDA(cudaFuncSetAttribute(group_union_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        group_union_smem_kernel<<<n_frames, GS_THREADS, smem, st>>>(cand, g.seg, g.parent, eps, (int)per_frame);
-    } else {
-        group_union_kernel<<<blocks, 256, 0, st>>>(cand, k, g.seg, g.parent, eps);
+    {
+        const long long nb = (k + GT - 1) / GT;
+        const long long tri = nb * (nb + 1) / 2;
+        RODC_CHECK_ARG(tri < (1ll << 31), "rodc_group_rectangles: too many candidates for one launch (%lld)", (long long)k);
+        group_union_kernel<<<(unsigned)tri, GT, 0, st>>>(cand, k, g.seg, g.parent, eps);
     }
     RODC_LAUNCH_CHECK();
     group_finalize_kernel<<<n_frames, 1024, 0, st>>>(cand, g.seg, g.parent, g.cls, g.sums, g.rrect, g.tmp, g.fcount, min_neighbors, eps);

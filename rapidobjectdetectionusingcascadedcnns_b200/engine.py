@@ -84,7 +84,7 @@ class CascadeEngine:
 
     # ------------------------------------------------------------------ stages on a window set
     def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
-                    keep_trace: bool, max_per_frame: int = 0) -> GroupResult:
+                    keep_trace: bool) -> GroupResult:
         dev = self.device
         impl = self._impl()
         n_st = len(self.stages)
@@ -137,18 +137,16 @@ class CascadeEngine:
                     final_conf = final_conf / np.float32(n_st)
                 elif mode_key == cf.FINAL_CONFIDENCE_CALCULATION_MULT:
                     final_conf = torch.clamp(final_conf, min=np.float32(cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT))
-                res = self._finish(res, meta, final_conf, kept, n_frames, max_per_frame)
+                res = self._finish(res, meta, final_conf, kept, n_frames)
         res.trace = trace
         return res
 
-    def _finish(self, res: GroupResult, meta: torch.Tensor, conf: torch.Tensor, k: int, n_frames: int,
-                max_per_frame: int = 0) -> GroupResult:
+    def _finish(self, res: GroupResult, meta: torch.Tensor, conf: torch.Tensor, k: int, n_frames: int) -> GroupResult:
         """``_postprocess_bboxes`` up to the vertical enlargement (done on the host by the app)."""
         if k == 0:
             return res
         if cf.get("nms") == cf.NMS_OPENCV:
-            out, count = native.group_rectangles(meta, k, n_frames, int(cf.get("nms_opencv_min_neighbors")), 0.2,
-                                                 max_per_frame=max_per_frame)
+            out, count = native.group_rectangles(meta, k, n_frames, int(cf.get("nms_opencv_min_neighbors")), 0.2)
             self.kernel_launches += 6
             kk = int(count.item())
             rows = out[:kk].cpu().numpy()
@@ -211,7 +209,7 @@ class CascadeEngine:
             self.kernel_launches += 1
             table = native.FrameTable.from_batch(frames)
             src0 = native.make_source(plan=plan, pyr=pyr)
-            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, max_per_frame=plan.n_windows)
+            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace)
 
     def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False) -> GroupResult:
         """``run_inference_on_windows``: caller-extracted stage-0 windows ``[n,S,S,3]`` u8 plus their
@@ -223,8 +221,7 @@ class CascadeEngine:
             table = native.FrameTable.from_list([torch.from_numpy(np.ascontiguousarray(f)).to(self.device) for f in frames])
             src0 = native.make_source(dense=wr)
             self._keepalive0 = (wr, m, table)
-            per_frame = int(np.bincount(np.asarray(meta, np.int64)[:, 0]).max()) if len(meta) else 0
-            return self._run_stages(src0, int(wr.shape[0]), m, table, len(frames), keep_trace, max_per_frame=per_frame)
+            return self._run_stages(src0, int(wr.shape[0]), m, table, len(frames), keep_trace)
 
     def softmax_on_raw(self, raw: np.ndarray) -> np.ndarray:
         """``run_inference_on_raw_data`` of the single net: softmax ``[n,2]`` for dense windows."""

@@ -274,8 +274,7 @@ def compact(probs: torch.Tensor, n: int, threshold: float, *, meta_in=None, meta
 
 
 # --------------------------------------------------------------------------------- group rectangles
-def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: int = 1, eps: float = 0.2,
-                     max_per_frame: int = 0):
+def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: int = 1, eps: float = 0.2):
     """K5.  cand ``[K,5]`` i32 (frame, xmin,ymin,xmax,ymax) grouped by frame ->
     ``(out [K,6] i32 (frame,x,y,w,h,weight), count i64 [1])`` on the device."""
     _require_cuda(cand)
@@ -284,6 +283,6 @@ def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: i
     count = torch.zeros((1,), dtype=torch.int64, device=dev)
     L = _lib.lib()
     scratch = torch.empty((int(L.rodc_group_scratch_bytes(int(k), int(n_frames))),), dtype=torch.uint8, device=dev)
-    check(L.rodc_group_rectangles(_ptr(cand), int(k), int(n_frames), int(max_per_frame), int(min_neighbors), float(eps), _ptr(out),
+    check(L.rodc_group_rectangles(_ptr(cand), int(k), int(n_frames), int(min_neighbors), float(eps), _ptr(out),
                                   _ptr(count), _ptr(scratch), _stream()), "rodc_group_rectangles")
     return out, count
