@@ -238,6 +238,12 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # BASELINE config 2 literally (ONE 640x480 frame per call): latency-bound, reported beside the batched value
+    one = d_frames[:1].contiguous()
+    for _ in range(3):
+        eng.run_frames(one)
+    ms_one = timed(lambda: eng.run_frames(one), 5) / 5.0
+
     if rank == 0:
         res = last["res"]
         frames_total = B * world * args.steps
@@ -264,6 +270,8 @@ def main():
                        "frames_per_step_per_gpu": B, "l2": "256 MiB flush buffer written between timed steps",
                        "fc1_impl": args.fc1, "parallelism": "image-sharded replicas x%d, NCCL all-gather of detections" % world},
             "windows_per_s": value * WINDOWS_PER_FRAME,
+            "single_frame": {"ms_per_frame": ms_one, "frames_per_s": 1000.0 / ms_one,
+                             "note": "one 640x480 frame per call (no batching): 5061 windows fill < 1 wave of 148 SMs"},
             "stage_in": res.stage_in, "stage_kept": res.stage_kept,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * FRAME_H * FRAME_W * 3,
                     "d2h_bytes_per_step": d2h, "boxes_per_step": n_boxes, "api": "InferenceCascadeApp.run_inference_on_images(merge=True)"},

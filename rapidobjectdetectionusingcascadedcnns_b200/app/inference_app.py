@@ -102,8 +102,9 @@ class InferenceApp(AbstractInferenceApp):
         out = [[] for _ in range(n_frames)]
         frames = res.frame.tolist()
         if post_nms:          # numpy ints and float(weight) like `:203-212`
-            for f, b, c in zip(frames, res.boxes, res.conf.tolist()):
-                x0, y0, x1, y1 = b
+            bx = res.boxes
+            for f, x0, y0, x1, y1, c in zip(frames, list(bx[:, 0]), list(bx[:, 1]), list(bx[:, 2]), list(bx[:, 3]),
+                                            res.conf.tolist()):
                 out[f].append(LabeledBoundingBox(x0, y0, x1, y1, fg, c, infos[f]))
         else:                 # python ints and the float32 softmax like cascade `:319-334`
             for f, b, c in zip(frames, res.boxes.tolist(), res.conf):

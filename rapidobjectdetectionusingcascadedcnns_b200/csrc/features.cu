@@ -110,146 +110,9 @@ __global__ void __launch_bounds__(128) recrop_kernel(SrcDev src, int64_t n, int 
     }
 }
 
-// ------------------------------------------------------------------ feature kernel
-// C = 32 channels; thread <-> (channel pair, 4-pixel row group); weights of the pair live in
-// registers for the whole window.  R = rows per strip (conv rows r0-1..r0+R kept in smem).
 constexpr int FEAT_THREADS = 256;
 
-template <int OUT_SPLIT>
-__global__ void __launch_bounds__(FEAT_THREADS)
-features_kernel(SrcDev src, int64_t first, int64_t n, int S, int R,
-                const float* __restrict__ conv_w, const float* __restrict__ conv_b,
-                float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    constexpr int C = 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P = S + 2;
-    float* inp = reinterpret_cast<float*>(smem_raw);                 // [P][P][3] zero-padded input
-    float* cbuf = inp + ((P * P * 3 + 3) & ~3);                      // [R+2][P][C] conv+ReLU, zero borders
-    int* tabs = reinterpret_cast<int*>(cbuf + (R + 2) * P * C);      // [6][S] recrop tables
-
-    const int64_t wrel = blockIdx.x;
-    if (wrel >= n) return;
-    const int64_t w = first + wrel;
-    const int tid = threadIdx.x;
-
-    // ---- 1. stage the u8 window as zero-padded floats
-    for (int i = tid; i < P * P * 3; i += FEAT_THREADS) inp[i] = 0.f;
-    for (int i = tid; i < (R + 2) * P * C; i += FEAT_THREADS) cbuf[i] = 0.f;
-    Crop crop;
-    if (src.kind == RODC_SRC_RECROP) { crop = make_crop(src, w); fill_recrop_tables(crop, S, tabs); }
-    __syncthreads();
-    if (src.kind == RODC_SRC_DENSE) {
-        const uint8_t* p = src.dense + w * (int64_t)S * S * 3;
-        for (int i = tid; i < S * S * 3; i += FEAT_THREADS) {
-            const int y = i / (S * 3), r = i - y * S * 3;
-            inp[((y + 1) * P + 1) * 3 + r] = (float)p[i];
-        }
-    } else if (src.kind == RODC_SRC_PYRAMID) {
-        const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
-        const int32_t* wr = src.win + j * 8;
-        const LevelInfo& lv = src.levels[wr[0]];
-        const uint8_t* p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
-        const int pitch = lv.w * 3;
-        for (int i = tid; i < S * S * 3; i += FEAT_THREADS) {
-            const int y = i / (S * 3), r = i - y * S * 3;
-            inp[((y + 1) * P + 1) * 3 + r] = (float)p[(int64_t)y * pitch + r];
-        }
-    } else {
-        for (int i = tid; i < S * S; i += FEAT_THREADS) {
-            const int y = i / S, x = i - y * S;
-            int px[3];
-            recrop_pixel(crop, S, tabs, y, x, px);
-            float* d = inp + ((y + 1) * P + (x + 1)) * 3;
-            d[0] = (float)px[0]; d[1] = (float)px[1]; d[2] = (float)px[2];
-        }
-    }
-
-    // ---- 2. weights of this thread's channel pair -> registers
-    const int cp = tid & 15;                 // channels 2cp, 2cp+1
-    float wreg[27][2];
-    #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        wreg[t][0] = __ldg(conv_w + t * C + 2 * cp);
-        wreg[t][1] = __ldg(conv_w + t * C + 2 * cp + 1);
-    }
-    const float b0 = __ldg(conv_b + 2 * cp), b1 = __ldg(conv_b + 2 * cp + 1);
-    __syncthreads();
-
-    const int XG = S >> 2;                   // 4-pixel groups per row (S is a multiple of 4)
-    float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C;
-    __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C : nullptr;
-    __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C : nullptr;
-
-    for (int r0 = 0; r0 < S; r0 += R) {
-        // ---- 3a. conv + bias + ReLU for rows r0-1 .. r0+R into cbuf rows 0 .. R+1
-        const int items = (R + 2) * XG * 16;
-        for (int it = tid; it < items; it += FEAT_THREADS) {
-            const int rest = it >> 4;
-            const int xg = rest % XG, ry = rest / XG;
-            const int y = r0 - 1 + ry;
-            float2* dst = reinterpret_cast<float2*>(cbuf + ((ry * P) + xg * 4 + 1) * C + 2 * cp);
-            if (y < 0 || y >= S) {
-                #pragma unroll
-                for (int px = 0; px < 4; ++px) dst[px * (C / 2)] = make_float2(0.f, 0.f);
-                continue;
-            }
-            float acc[4][2];
-            #pragma unroll
-            for (int px = 0; px < 4; ++px) { acc[px][0] = b0; acc[px][1] = b1; }
-            #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const float* row = inp + ((y + ky) * P + xg * 4) * 3;
-                float v[18];
-                #pragma unroll
-                for (int q = 0; q < 18; ++q) v[q] = row[q];
-                #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-                    #pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) {
-                        const int t = (ky * 3 + kx) * 3 + ci;
-                        #pragma unroll
-                        for (int px = 0; px < 4; ++px) {
-                            acc[px][0] = fmaf(v[(px + kx) * 3 + ci], wreg[t][0], acc[px][0]);
-                            acc[px][1] = fmaf(v[(px + kx) * 3 + ci], wreg[t][1], acc[px][1]);
-                        }
-                    }
-            }
-            #pragma unroll
-            for (int px = 0; px < 4; ++px)
-                dst[px * (C / 2)] = make_float2(fmaxf(acc[px][0], 0.f), fmaxf(acc[px][1], 0.f));
-        }
-        __syncthreads();
-        // ---- 3b. maxpool 3x3 + store (rows r0 .. r0+R-1)
-        const int rows = min(R, S - r0);
-        const int pitems = rows * S * 16;
-        for (int it = tid; it < pitems; it += FEAT_THREADS) {
-            const int rest = it >> 4;
-            const int x = rest % S, r = rest / S;
-            const float2* c0 = reinterpret_cast<const float2*>(cbuf + ((r * P) + x) * C + 2 * cp);
-            float2 m = make_float2(0.f, 0.f);
-            #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-                #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float2 q = c0[(dy * P + dx) * (C / 2)];
-                    m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y);
-                }
-            const int64_t k = ((int64_t)(r0 + r) * S + x) * C + 2 * cp;
-            if (OUT_SPLIT) {
-                const float sx = m.x * a_scale, sy = m.y * a_scale;          // exact: power of two
-                const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy);
-                const __half lx = __float2half_rn(sx - __half2float(hx)), ly = __float2half_rn(sy - __half2float(hy));
-                *reinterpret_cast<__half2*>(oh + k) = __halves2half2(hx, hy);
-                *reinterpret_cast<__half2*>(ol + k) = __halves2half2(lx, ly);
-            } else {
-                *reinterpret_cast<float2*>(of + k) = m;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------ feature kernel v2 (tensor-core conv)
+// ------------------------------------------------------------------ feature kernel, generic sizes (smem pooling)
 // The 3x3x3 -> 32 convolution is a [pixels x 48] x [48 x 32] GEMM per window: K = 3 filter rows x
 // (4 pixels x 4 channels), where the 4th pixel / 4th channel carry zero weights so that the A row of
 // a pixel is ONE contiguous 32-byte run of the fp16 input staged as [P][P][4] -- the im2col matrix is
@@ -441,8 +304,8 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
     }
 }
 
-// ------------------------------------------------------------------ feature kernel v3 (streaming, barrier free)
-// Same arithmetic as v2, but the conv output never touches shared memory: warp (cg, part) owns 16
+// ------------------------------------------------------------------ feature kernel, 12 / 24 / 48 (streaming, barrier free)
+// Same arithmetic as the generic kernel, but the conv output never touches shared memory: warp (cg, part) owns 16
 // channels x one quarter of the window rows and streams down its rows.  M row r of an MMA tile maps to
 // pixel 16j + 2 (r % 8) + r / 8, so every thread holds two horizontally adjacent pixels and the
 // horizontal 3-max needs just two lane shuffles per value; the vertical 3-max is a sliding window of
@@ -661,18 +524,6 @@ static int pick_rows2(int S) {
     return 4;
 }
 
-static size_t feat_smem_bytes(int S, int R) {
-    const int P = S + 2;
-    return (size_t)((P * P * 3 + 3) & ~3) * 4 + (size_t)(R + 2) * P * 32 * 4 + (size_t)6 * S * 4;
-}
-
-static int pick_rows(int S) {
-    // largest multiple-of-4 strip that keeps two CTAs per SM (<= 112 KB each)
-    for (int R = S; R > 4; R -= 4)
-        if (feat_smem_bytes(S, R) <= 112 * 1024) return R;
-    return 4;
-}
-
 int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     RODC_CHECK_ARG(src != nullptr, "window source is NULL");
     SrcDev d; memset(&d, 0, sizeof(d));
@@ -699,12 +550,6 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     return RODC_OK;
 }
 
-static bool use_legacy_features() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("RODC_FEATURES_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
                     float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st) {
     if (n <= 0) return RODC_OK;
@@ -713,24 +558,12 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
     RODC_CHECK_ARG(n < (1ll << 31), "too many windows in one launch");
     const int S = s->in_size;
     const float a_scale = ldexpf(1.f, s->a_exp);
-    if (use_legacy_features()) {          // CUDA-core conv (first implementation, kept as a cross-check)
-        const int R = pick_rows(S);
-        const size_t smem = feat_smem_bytes(S, R);
-        if (out_f32) {
-            RODC_CUDA(cudaFuncSetAttribute(features_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            features_kernel<0><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, out_f32, nullptr, nullptr);
-        } else {
-            RODC_CUDA(cudaFuncSetAttribute(features_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            features_kernel<1><<<(unsigned)n, FEAT_THREADS, smem, st>>>(src, first, n, S, R, s->conv_w, s->conv_b, a_scale, nullptr, out_hi, out_lo);
-        }
-        RODC_LAUNCH_CHECK();
-        return RODC_OK;
-    }
     const float conv_scale = ldexpf(1.f, -s->c_exp);
     // persistent-style grid: two CTAs per SM, each loops over windows
     const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
+    // RODC_FEATURES_GENERIC=1 forces the generic kernel (cross-check of the specialised one)
     static int use_v2 = -1;
-    if (use_v2 < 0) { const char* e = getenv("RODC_FEATURES_V2"); use_v2 = (e && e[0] == '1') ? 1 : 0; }
+    if (use_v2 < 0) { const char* e = getenv("RODC_FEATURES_GENERIC"); use_v2 = (e && e[0] == '1') ? 1 : 0; }
     if (!use_v2 && (S == 12 || S == 24 || S == 48)) {
 #define RODC_LAUNCH_FEAT3(SPLIT, ST_)                                                                                      \
         do {                                                                                                              \
@@ -752,17 +585,7 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         features_mma_kernel<SPLIT, ST_, RT_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, Rv, s->conv_frag, s->conv_b, \
                                                                                 conv_scale, a_scale, out_f32, out_hi, out_lo); \
     } while (0)
-    if (out_f32) {
-        if (S == 12) RODC_LAUNCH_FEAT(0, 12, 12, 12);
-        else if (S == 24) RODC_LAUNCH_FEAT(0, 24, 12, 12);
-        else if (S == 48) RODC_LAUNCH_FEAT(0, 48, 8, 8);
-        else { const int R = pick_rows2(S); RODC_LAUNCH_FEAT(0, 0, 0, R); }
-    } else {
-        if (S == 12) RODC_LAUNCH_FEAT(1, 12, 12, 12);
-        else if (S == 24) RODC_LAUNCH_FEAT(1, 24, 12, 12);
-        else if (S == 48) RODC_LAUNCH_FEAT(1, 48, 8, 8);
-        else { const int R = pick_rows2(S); RODC_LAUNCH_FEAT(1, 0, 0, R); }
-    }
+    { const int R = pick_rows2(S); if (out_f32) RODC_LAUNCH_FEAT(0, 0, 0, R); else RODC_LAUNCH_FEAT(1, 0, 0, R); }
 #undef RODC_LAUNCH_FEAT
     RODC_LAUNCH_CHECK();
     return RODC_OK;

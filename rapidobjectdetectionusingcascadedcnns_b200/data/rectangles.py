@@ -11,6 +11,8 @@ from typing import List
 
 
 class Rectangle:
+    __slots__ = ("_xmin", "_ymin", "_xmax", "_ymax")
+
     def __init__(self, xmin, ymin, xmax, ymax):
         self._xmin, self._ymin, self._xmax, self._ymax = xmin, ymin, xmax, ymax
 
@@ -58,13 +60,16 @@ class Rectangle:
 
 
 class BoundingBox(Rectangle):
-    pass
+    __slots__ = ()
 
 
 class LabeledBoundingBox(BoundingBox):
+    __slots__ = ("_xmin", "_ymin", "_xmax", "_ymax", "_label", "_confidence", "_image")
+
     def __init__(self, xmin, ymin, xmax, ymax, label, confidence=0.0, image=None):
-        self._label, self._confidence, self._image = label, confidence, image
-        BoundingBox.__init__(self, xmin, ymin, xmax, ymax)
+        # flat initialisation (thousands of boxes per batch are built on the host)
+        self._xmin = xmin; self._ymin = ymin; self._xmax = xmax; self._ymax = ymax
+        self._label = label; self._confidence = confidence; self._image = image
 
     @property
     def label(self):
@@ -95,6 +100,8 @@ class LabeledBoundingBox(BoundingBox):
 
 
 class Window(Rectangle):
+    __slots__ = ("_image", "_scale")
+
     def __init__(self, xmin, ymin, xmax, ymax, image, scale=1.0):
         self._image, self._scale = image, scale
         Rectangle.__init__(self, xmin, ymin, xmax, ymax)

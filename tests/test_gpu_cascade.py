@@ -184,3 +184,29 @@ def test_full_size_properties_640x480_batch(pkg):
     res2 = eng.run_frames(frames)
     assert np.array_equal(res.boxes, res2.boxes) and np.array_equal(res.conf, res2.conf)
     assert res.stage_in[1:] == res.stage_kept[:-1]
+
+
+def test_non_default_stage_sizes_use_generic_kernel(pkg):
+    """A 2-stage cascade with 16/32-px inputs (img_max 32): exercises the generic feature kernel and the
+    planner with another window size, end to end against the fp64 oracle."""
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    pkg.cf.set("min_window_length", 0.2)
+    ocfg = oc.Config(min_window_length=0.2)
+    base = synth.xavier_cascade(2, img_max=32)
+    frames = [synth.synth_frame(130, 170, 21), synth.synth_frame(130, 170, 22)]
+    offsets = oc.calibrate_offsets(frames[:1], base, ocfg, [0.4, 0.5])
+    weights = synth.xavier_cascade(2, img_max=32, fg_bias_offsets=offsets)
+    assert [w["fc1_W"].shape[0] for w in weights] == [16 * 16 * 32, 32 * 32 * 32]
+    app = pkg.InferenceCascadeApp("g", stage_models=[pkg.StageModel(w) for w in weights])
+    got = app.run_inference_on_images([pkg.ArrayImageInfo(f, "g%d.png" % i) for i, f in enumerate(frames)], merge=True)
+    g = np.asarray([[i, b.xmin, b.ymin, b.xmax, b.ymax, b.confidence] for i, per in enumerate(got) for b in per],
+                   np.float64).reshape(-1, 6)
+    r = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64)
+    ref = np.column_stack([r.image, r.boxes, r.conf]).astype(np.float64).reshape(-1, 6)
+    res = app._engine.run_frames(np.stack(frames), keep_trace=True)
+    for i, st in enumerate(r.stages):
+        lg = res.trace["logits"][i].cpu().numpy()
+        assert np.abs(lg - st.logits).max() <= 1e-3 * np.abs(st.logits).max()
+        assert np.array_equal(res.trace["keep"][i].cpu().numpy(), st.keep_idx)
+    assert np.array_equal(g, ref)
