@@ -308,17 +308,19 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
 // Same arithmetic as the generic kernel, but the conv output never touches shared memory: warp (cg, part) owns 16
 // channels x one quarter of the window rows and streams down its rows.  M row r of an MMA tile maps to
 // pixel 16j + 2 (r % 8) + r / 8, so every thread holds two horizontally adjacent pixels and the
-// horizontal 3-max needs just two lane shuffles per value; the vertical 3-max is a sliding window of
-// three row registers.  The two n-tiles of a warp use permuted weight columns so that thread t owns
+// horizontal 3-max needs two lane shuffles per channel and row (pixel x = 2 TR g + i: a thread owns 2 TR
+// adjacent pixels); the vertical 3-max is a sliding window of row registers.  Pixels are staged as
+// (r, g, b, 1) * 2^(a_exp - c_exp): the constant channel carries the bias through the MMA and the
+// accumulator IS the feature scaled for the fp16 split; the ReLU is applied once after the pooling.  The two n-tiles of a warp use permuted weight columns so that thread t owns
 // channels 4t..4t+3 of its group: stores are 8-byte, four lanes fill one 32-byte sector.  One
 // __syncthreads per window (input staging is double buffered).  This is also the producer the fused
 // feature->fc1 kernel needs (round 2): only the final store changes.
 template <int OUT_SPLIT, int S>
 __global__ void __launch_bounds__(FEAT_THREADS, 2)
 features_stream_kernel(SrcDev src, int64_t first, int64_t n,
-                       const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
-                       float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NQ = 4, RQ = S / NQ;
+                       const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
+                       float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NQ = 4, RQ = S / NQ, NP = 2 * TR;   // NP pixels per thread and row
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* inh0 = reinterpret_cast<__half*>(smem_raw);
@@ -328,8 +330,10 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
     const int g = lane >> 2, t = lane & 3;
     const int cg = warp & 1, part = warp >> 1;
     const int ya = part * RQ, yb = ya + RQ;
+    const int xbase = NP * g;                                             // this thread's pixels: xbase .. xbase + NP - 1
+    const bool lane_in = xbase < S;                                      // S = 24 / 12 leave lane groups 6, 7 idle
 
-    // B fragments of this warp's two n-tiles (permuted columns, see stage.cu) and its 4 biases
+    // B fragments of this warp's two n-tiles (permuted columns, bias folded into the spare K slot)
     uint32_t bf[3][2][2][2];
     #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
@@ -340,15 +344,13 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
                 const uint2 v = __ldg(reinterpret_cast<const uint2*>(conv_frag) + (((ky * 4 + (cg * 2 + sub)) * 2 + h) * 32 + lane));
                 bf[ky][sub][h][0] = v.x; bf[ky][sub][h][1] = v.y;
             }
-    float bias4[4];
-    #pragma unroll
-    for (int c = 0; c < 4; ++c) bias4[c] = __ldg(conv_b + 16 * cg + 4 * t + c);
+    const __half one_h = __float2half_rn(pix_scale);
 
     int iter = 0;
     for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x, ++iter) {
         const int64_t w = first + wrel;
         __half* inh = inh0 + (size_t)(iter & 1) * INH;
-        // ---- stage the window as zero-padded fp16 [P][P][4]
+        // ---- stage the window as fp16 [P][P][4] = (r, g, b, 1) * 2^p, zero border
         {
             uint4* z = reinterpret_cast<uint4*>(inh);
             for (int i = tid; i < INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -365,8 +367,8 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
                 int px[3];
                 recrop_pixel(crop, S, tabs, y, x, px);
                 __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
-                d[0] = __halves2half2(__int2half_rn(px[0]), __int2half_rn(px[1]));
-                d[1] = __halves2half2(__int2half_rn(px[2]), __int2half_rn(0));
+                d[0] = __floats2half2_rn((float)px[0] * pix_scale, (float)px[1] * pix_scale);
+                d[1] = __halves2half2(__float2half_rn((float)px[2] * pix_scale), one_h);
             }
         } else {
             const uint8_t* p; int pitch;
@@ -382,36 +384,36 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
                 const int y = i / S, x = i - y * S;
                 const uint8_t* q = p + (int64_t)y * pitch + x * 3;
                 __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
-                d[0] = __halves2half2(__int2half_rn((int)q[0]), __int2half_rn((int)q[1]));
-                d[1] = __halves2half2(__int2half_rn((int)q[2]), __int2half_rn(0));
+                d[0] = __floats2half2_rn((float)q[0] * pix_scale, (float)q[1] * pix_scale);
+                d[1] = __halves2half2(__float2half_rn((float)q[2] * pix_scale), one_h);
             }
         }
         __syncthreads();                                       // window staged
 
-        float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C;
-        __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C : nullptr;
-        __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C : nullptr;
+        // thread-constant output pointers (row offset added per row, pixel offsets are immediates)
+        const int64_t tofs = (int64_t)xbase * C + 16 * cg + 4 * t;
+        float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C + tofs;
+        __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C + tofs : nullptr;
+        __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C + tofs : nullptr;
+        const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + (lane_in ? xbase : 0) * 4) + t;
 
-        // sliding window of horizontal maxima: [tile][pixel 0/1][4 channels]
-        float hA[TR][2][4], hB[TR][2][4];                      // max(h[y-2], h[y-1]) and h[y-1]
+        // sliding window of horizontal maxima of (conv + bias) * 2^a_exp, BEFORE the ReLU: the ReLU commutes
+        // with the max and is applied once at the output as max(., 0); zeros stand for SAME padding.
+        float hA[NP][4], hB[NP][4];                            // max(h[y-2], h[y-1]) and h[y-1]
         #pragma unroll
-        for (int j = 0; j < TR; ++j)
+        for (int i = 0; i < NP; ++i)
             #pragma unroll
-            for (int q = 0; q < 2; ++q)
-                #pragma unroll
-                for (int c = 0; c < 4; ++c) { hA[j][q][c] = 0.f; hB[j][q][c] = 0.f; }
+            for (int c = 0; c < 4; ++c) { hA[i][c] = 0.f; hB[i][c] = 0.f; }
 
         #pragma unroll 1
         for (int yy = ya - 1; yy <= yb; ++yy) {
-            float v[TR][2][4];
-            const bool row_in = yy >= 0 && yy < S;
-            if (row_in) {
+            float hc[NP][4];
+            if (yy >= 0 && yy < S) {
+                float v[NP][4];
                 #pragma unroll
                 for (int j = 0; j < TR; ++j) {
-                    // A rows: pixel x0 = 16 j + 2 g (fragment row g) and x0 + 1 (row g + 8)
-                    const int x0 = 16 * j + 2 * g;
-                    const int xc = x0 < S ? x0 : 0;             // masked tiles read pixel 0 (finite), zeroed below
-                    const uint32_t* base = reinterpret_cast<const uint32_t*>(inh + ((yy * P) + xc) * 4) + t;
+                    // fragment row g -> pixel xbase + 2 j, row g + 8 -> pixel xbase + 2 j + 1
+                    const uint32_t* base = abase + (yy * P + 2 * j) * 2;
                     float acc[2][4];
                     #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) { acc[sub][0] = acc[sub][1] = acc[sub][2] = acc[sub][3] = 0.f; }
@@ -425,82 +427,68 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
                             mma16816(acc[sub], a0, a1, a2, a3, bf[ky][sub][0][0], bf[ky][sub][0][1]);
                         }
                     }
-                    const bool in0 = x0 < S, in1 = x0 + 1 < S;
+                    const bool in0 = xbase + 2 * j < S, in1 = xbase + 2 * j + 1 < S;
                     #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
-                        v[j][0][2 * sub + 0] = in0 ? fmaxf(fmaf(acc[sub][0], conv_scale, bias4[2 * sub + 0]), 0.f) : 0.f;
-                        v[j][0][2 * sub + 1] = in0 ? fmaxf(fmaf(acc[sub][1], conv_scale, bias4[2 * sub + 1]), 0.f) : 0.f;
-                        v[j][1][2 * sub + 0] = in1 ? fmaxf(fmaf(acc[sub][2], conv_scale, bias4[2 * sub + 0]), 0.f) : 0.f;
-                        v[j][1][2 * sub + 1] = in1 ? fmaxf(fmaf(acc[sub][3], conv_scale, bias4[2 * sub + 1]), 0.f) : 0.f;
+                        v[2 * j][2 * sub + 0] = in0 ? acc[sub][0] : 0.f;
+                        v[2 * j][2 * sub + 1] = in0 ? acc[sub][1] : 0.f;
+                        v[2 * j + 1][2 * sub + 0] = in1 ? acc[sub][2] : 0.f;
+                        v[2 * j + 1][2 * sub + 1] = in1 ? acc[sub][3] : 0.f;
+                    }
+                }
+                // horizontal 3-max: only the first / last pixel of a thread need a neighbour lane
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float ln = __shfl_sync(0xffffffffu, v[NP - 1][c], (lane + 28) & 31);   // last pixel of lane group g-1
+                    float rn = __shfl_sync(0xffffffffu, v[0][c], (lane + 4) & 31);         // first pixel of lane group g+1
+                    ln = g > 0 ? ln : 0.f;
+                    rn = g < 7 ? rn : 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const float l = i > 0 ? v[i > 0 ? i - 1 : 0][c] : ln;
+                        const float r = i < NP - 1 ? v[i < NP - 1 ? i + 1 : i][c] : rn;
+                        hc[i][c] = fmaxf(fmaxf(l, v[i][c]), r);
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int i = 0; i < NP; ++i)
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) hc[i][c] = 0.f;
+            }
+            // vertical: pooled row yy-1 = relu(max(h[yy-2], h[yy-1], h[yy]))
+            const int yo = yy - 1;
+            if (yo >= ya && yo < yb && lane_in) {
+                const int64_t rofs = (int64_t)yo * S * C;
+                #pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    if (xbase + i < S) {
+                        float m[4];
+                        #pragma unroll
+                        for (int c = 0; c < 4; ++c) m[c] = fmaxf(fmaxf(hA[i][c], hc[i][c]), 0.f);
+                        if (OUT_SPLIT) {
+                            const __half2 h01 = __floats2half2_rn(m[0], m[1]), h23 = __floats2half2_rn(m[2], m[3]);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(m[0] - f01.x, m[1] - f01.y), l23 = __floats2half2_rn(m[2] - f23.x, m[3] - f23.y);
+                            uint2 uh, ul;
+                            uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(oh + rofs + i * C) = uh;
+                            *reinterpret_cast<uint2*>(ol + rofs + i * C) = ul;
+                        } else {
+                            *reinterpret_cast<float4*>(of + rofs + i * C) =
+                                make_float4(m[0] * inv_a_scale, m[1] * inv_a_scale, m[2] * inv_a_scale, m[3] * inv_a_scale);
+                        }
                     }
                 }
             }
-            // horizontal 3-max (zero outside the window == SAME padding for post-ReLU data)
-            float hc[TR][2][4];
-            if (row_in) {
-                float R[TR][4], L[TR][4];
-                #pragma unroll
-                for (int j = 0; j < TR; ++j)
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        R[j][c] = __shfl_sync(0xffffffffu, v[j][0][c], (lane + 4) & 31);    // first pixel of lane g+1 (wraps to g=0)
-                        L[j][c] = __shfl_sync(0xffffffffu, v[j][1][c], (lane + 28) & 31);   // second pixel of lane g-1 (wraps to g=7)
-                    }
-                #pragma unroll
-                for (int j = 0; j < TR; ++j)
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float rn = (g < 7) ? R[j][c] : (j + 1 < TR ? R[(j + 1 < TR) ? j + 1 : j][c] : 0.f);
-                        const float ln = (g > 0) ? L[j][c] : (j > 0 ? L[(j > 0) ? j - 1 : j][c] : 0.f);
-                        hc[j][0][c] = fmaxf(fmaxf(ln, v[j][0][c]), v[j][1][c]);
-                        hc[j][1][c] = fmaxf(fmaxf(v[j][0][c], v[j][1][c]), rn);
-                    }
-            } else {
-                #pragma unroll
-                for (int j = 0; j < TR; ++j)
-                    #pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        #pragma unroll
-                        for (int c = 0; c < 4; ++c) hc[j][q][c] = 0.f;
-            }
-            // vertical: pooled row yy-1 = max(h[yy-2], h[yy-1], h[yy])
-            const int yo = yy - 1;
-            if (yo >= ya && yo < yb) {
-                #pragma unroll
-                for (int j = 0; j < TR; ++j)
-                    #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int x = 16 * j + 2 * g + q;
-                        if (x < S) {
-                            float m[4];
-                            #pragma unroll
-                            for (int c = 0; c < 4; ++c) m[c] = fmaxf(hA[j][q][c], hc[j][q][c]);
-                            const int64_t k = ((int64_t)yo * S + x) * C + 16 * cg + 4 * t;
-                            if (OUT_SPLIT) {
-                                const float s0 = m[0] * a_scale, s1 = m[1] * a_scale, s2 = m[2] * a_scale, s3 = m[3] * a_scale;
-                                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
-                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
-                                uint2 uh, ul;
-                                uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
-                                ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-                                *reinterpret_cast<uint2*>(oh + k) = uh;
-                                *reinterpret_cast<uint2*>(ol + k) = ul;
-                            } else {
-                                *reinterpret_cast<float4*>(of + k) = make_float4(m[0], m[1], m[2], m[3]);
-                            }
-                        }
-                    }
-            }
             #pragma unroll
-            for (int j = 0; j < TR; ++j)
+            for (int i = 0; i < NP; ++i)
                 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        hA[j][q][c] = fmaxf(hB[j][q][c], hc[j][q][c]);
-                        hB[j][q][c] = hc[j][q][c];
-                    }
+                for (int c = 0; c < 4; ++c) {
+                    hA[i][c] = fmaxf(hB[i][c], hc[i][c]);
+                    hB[i][c] = hc[i][c];
+                }
         }
     }
 }
@@ -569,8 +557,9 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         do {                                                                                                              \
             const size_t smem = feat3_smem_bytes<ST_>();                                                                  \
             RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->conv_frag_perm, s->conv_b,  \
-                                                                                 conv_scale, a_scale, out_f32, out_hi, out_lo); \
+            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->conv_frag_perm,           \
+                                                                                 ldexpf(1.f, s->a_exp - s->c_exp),          \
+                                                                                 ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo); \
         } while (0)
         if (out_f32) { if (S == 12) RODC_LAUNCH_FEAT3(0, 12); else if (S == 24) RODC_LAUNCH_FEAT3(0, 24); else RODC_LAUNCH_FEAT3(0, 48); }
         else { if (S == 12) RODC_LAUNCH_FEAT3(1, 12); else if (S == 24) RODC_LAUNCH_FEAT3(1, 24); else RODC_LAUNCH_FEAT3(1, 48); }

@@ -157,7 +157,12 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
     {
         double cmax = 0.0;
         for (size_t i = 0; i < nconv; ++i) { double a = fabs((double)conv_w[i]); if (a > cmax) cmax = a; }
+        for (int c = 0; c < conv_channels; ++c) { double a = fabs((double)conv_b[c]); if (a > cmax) cmax = a; }   // bias rides in a K slot
         s->c_exp = pow2_headroom(cmax, 16384.0);
+        // the streaming feature kernel stages pixels as u8 * 2^(a_exp - c_exp) in fp16: keep that exponent
+        // inside the fp16 normal range (always true for sane nets: it is about -7 .. -12)
+        if (s->a_exp - s->c_exp < -14) s->c_exp = s->a_exp + 14;
+        if (s->a_exp - s->c_exp > 7) s->c_exp = s->a_exp - 7;
         const float cs = ldexpf(1.f, s->c_exp);
         std::vector<uint32_t> frag((size_t)3 * 4 * 2 * 32 * 2, 0u), fragp(frag.size(), 0u);
         auto wval = [&](int ky, int j, int nn) -> float {
@@ -184,7 +189,9 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
                             // permuted variant (features v3): n-tile nt = 2*cg + sub, column gg -> channel
                             // 16*cg + 4*(gg/2) + 2*sub + gg%2, so lane t owns channels 4t..4t+3 of its group
                             const int np = 16 * (nt >> 1) + 4 * (gg >> 1) + 2 * (nt & 1) + (gg & 1);
-                            const uint32_t plo = halfbits(wval(ky, j0, np), h), phi = halfbits(wval(ky, j0 + 1, np), h);
+                            // K slot (ky = 1, kx = 1, ci = 3) multiplies the constant-one channel of the centre pixel: bias
+                            auto wvalb = [&](int jj) -> float { return (ky == 1 && jj == 7) ? conv_b[np] * cs : wval(ky, jj, np); };
+                            const uint32_t plo = halfbits(wvalb(j0), h), phi = halfbits(wvalb(j0 + 1), h);
                             fragp[((((size_t)(ky * 4 + nt) * 2 + h) * 32) + lane) * 2 + r] = plo | (phi << 16);
                         }
                     }
