@@ -80,6 +80,8 @@ def test_cascade_app_matches_reference_run(pkg, name, impl):
                 assert np.abs(margin).max() < EPS[i], "stage %d: survivor flip outside the epsilon band: %r" % (i, margin)
             n_checked += 1
         assert n_checked >= 1
+    # the golden cases were chosen without near-threshold windows: on B200 every survivor set matches
+    assert same_survivors, "a golden case flipped a survivor (inside the epsilon band) -- regenerate or inspect"
     if same_survivors:
         ref = g["final_boxes"]
         assert got.shape == ref.shape
