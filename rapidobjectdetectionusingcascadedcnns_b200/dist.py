@@ -28,17 +28,19 @@ def gather_detections(rows: np.ndarray, device=None) -> np.ndarray:
     ws = dist.get_world_size()
     backend = dist.get_backend()
     dev = torch.device("cpu") if backend == "gloo" else (device or torch.device("cuda", torch.cuda.current_device()))
+    # two collectives and two host reads in total: counts, then one padded [ws * Kmax, 6] block
     cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(cnt) for _ in range(ws)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
+    counts_t = torch.empty((ws,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, cnt)
+    counts = counts_t.cpu().tolist()
     kmax = max(max(counts), 1)
     pad = torch.zeros((kmax, 6), dtype=torch.float64, device=dev)
     if rows.shape[0]:
         pad[:rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(rows, np.float64)).to(dev)
-    bufs = [torch.zeros_like(pad) for _ in range(ws)]
-    dist.all_gather(bufs, pad)
-    parts = [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
+    allbuf = torch.empty((ws * kmax, 6), dtype=torch.float64, device=dev)     # concatenated along dim 0
+    dist.all_gather_into_tensor(allbuf, pad)
+    host = allbuf.cpu().numpy().reshape(ws, kmax, 6)
+    parts = [host[r, :c] for r, c in enumerate(counts)]
     allrows = np.concatenate(parts) if parts else np.zeros((0, 6))
     order = np.argsort(allrows[:, 0], kind="stable")
     return allrows[order]
