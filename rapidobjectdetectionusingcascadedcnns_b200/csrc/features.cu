@@ -315,20 +315,26 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
 // channels 4t..4t+3 of its group: stores are 8-byte, four lanes fill one 32-byte sector.  One
 // __syncthreads per window (input staging is double buffered).  This is also the producer the fused
 // feature->fc1 kernel needs (round 2): only the final store changes.
+// Warp layout per window size (8 warps): S = 48 -> 1 window x 4 row parts x 2 channel groups;
+// S = 24 -> 2 windows x 2 parts x 2 groups; S = 12 -> 4 windows x 1 part x 2 groups, so small
+// windows are not dominated by the one-row halo that every row part recomputes.
+template <int S> struct StreamCfg { static constexpr int NQ = S >= 48 ? 4 : (S >= 24 ? 2 : 1); static constexpr int WPC = 4 / NQ; };
+
 template <int OUT_SPLIT, int S>
 __global__ void __launch_bounds__(FEAT_THREADS, 2)
 features_stream_kernel(SrcDev src, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NQ = 4, RQ = S / NQ, NP = 2 * TR;   // NP pixels per thread and row
+    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NP = 2 * TR;    // NP pixels per thread and row
+    constexpr int NQ = StreamCfg<S>::NQ, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* inh0 = reinterpret_cast<__half*>(smem_raw);
-    int* tabs = reinterpret_cast<int*>(smem_raw + (size_t)2 * INH * 2);
+    __half* inh0 = reinterpret_cast<__half*>(smem_raw);                  // [2 buffers][WPC windows][INH]
+    int* tabs0 = reinterpret_cast<int*>(smem_raw + (size_t)2 * WPC * INH * 2);   // [WPC][6 S]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int cg = warp & 1, part = warp >> 1;
+    const int cg = warp & 1, part = (warp >> 1) % NQ, slot = (warp >> 1) / NQ;
     const int ya = part * RQ, yb = ya + RQ;
     const int xbase = NP * g;                                             // this thread's pixels: xbase .. xbase + NP - 1
     const bool lane_in = xbase < S;                                      // S = 24 / 12 leave lane groups 6, 7 idle
@@ -347,48 +353,54 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
     const __half one_h = __float2half_rn(pix_scale);
 
     int iter = 0;
-    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x, ++iter) {
-        const int64_t w = first + wrel;
-        __half* inh = inh0 + (size_t)(iter & 1) * INH;
-        // ---- stage the window as fp16 [P][P][4] = (r, g, b, 1) * 2^p, zero border
+    for (int64_t wrel0 = (int64_t)blockIdx.x * WPC; wrel0 < n; wrel0 += (int64_t)gridDim.x * WPC, ++iter) {
+        __half* inhb = inh0 + (size_t)(iter & 1) * WPC * INH;
+        // ---- stage WPC windows as fp16 [P][P][4] = (r, g, b, 1) * 2^p, zero border
         {
-            uint4* z = reinterpret_cast<uint4*>(inh);
-            for (int i = tid; i < INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* z = reinterpret_cast<uint4*>(inhb);
+            for (int i = tid; i < WPC * INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        Crop crop;
         if (src.kind == RODC_SRC_RECROP) {
-            crop = make_crop(src, w);
-            fill_recrop_tables(crop, S, tabs);                 // safe: everyone left the previous window's staging
+            for (int sl = 0; sl < WPC; ++sl)
+                if (wrel0 + sl < n) {
+                    const Crop c = make_crop(src, first + wrel0 + sl);
+                    fill_recrop_tables(c, S, tabs0 + sl * 6 * S);      // safe: everyone left the previous staging
+                }
         }
         __syncthreads();                                       // zero fill (and tables) visible
-        if (src.kind == RODC_SRC_RECROP) {
-            for (int i = tid; i < S * S; i += FEAT_THREADS) {
-                const int y = i / S, x = i - y * S;
+        for (int i = tid; i < WPC * S * S; i += FEAT_THREADS) {
+            const int sl = i / (S * S), r = i - sl * S * S;
+            if (wrel0 + sl >= n) continue;
+            const int64_t w = first + wrel0 + sl;
+            const int y = r / S, x = r - y * S;
+            float p0, p1, p2;
+            if (src.kind == RODC_SRC_RECROP) {
+                const Crop c = make_crop(src, w);
                 int px[3];
-                recrop_pixel(crop, S, tabs, y, x, px);
-                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
-                d[0] = __floats2half2_rn((float)px[0] * pix_scale, (float)px[1] * pix_scale);
-                d[1] = __halves2half2(__float2half_rn((float)px[2] * pix_scale), one_h);
-            }
-        } else {
-            const uint8_t* p; int pitch;
-            if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
-            else {
-                const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
-                const int32_t* wr = src.win + j * 8;
-                const LevelInfo& lv = src.levels[wr[0]];
-                p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
-                pitch = lv.w * 3;
-            }
-            for (int i = tid; i < S * S; i += FEAT_THREADS) {
-                const int y = i / S, x = i - y * S;
+                recrop_pixel(c, S, tabs0 + sl * 6 * S, y, x, px);
+                p0 = (float)px[0]; p1 = (float)px[1]; p2 = (float)px[2];
+            } else {
+                const uint8_t* p; int pitch;
+                if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+                else {
+                    const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
+                    const int32_t* wr = src.win + j * 8;
+                    const LevelInfo& lv = src.levels[wr[0]];
+                    p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+                    pitch = lv.w * 3;
+                }
                 const uint8_t* q = p + (int64_t)y * pitch + x * 3;
-                __half2* d = reinterpret_cast<__half2*>(inh + ((y + 1) * P + (x + 1)) * 4);
-                d[0] = __floats2half2_rn((float)q[0] * pix_scale, (float)q[1] * pix_scale);
-                d[1] = __halves2half2(__float2half_rn((float)q[2] * pix_scale), one_h);
+                p0 = (float)q[0]; p1 = (float)q[1]; p2 = (float)q[2];
             }
+            __half2* d = reinterpret_cast<__half2*>(inhb + (size_t)sl * INH + ((y + 1) * P + (x + 1)) * 4);
+            d[0] = __floats2half2_rn(p0 * pix_scale, p1 * pix_scale);
+            d[1] = __halves2half2(__float2half_rn(p2 * pix_scale), one_h);
         }
-        __syncthreads();                                       // window staged
+        __syncthreads();                                       // windows staged
+
+        const int64_t wrel = wrel0 + slot;
+        if (wrel >= n) continue;                               // tail: this warp's window slot is empty
+        const __half* inh = inhb + (size_t)slot * INH;
 
         // thread-constant output pointers (row offset added per row, pixel offsets are immediates)
         const int64_t tofs = (int64_t)xbase * C + 16 * cg + 4 * t;
@@ -497,7 +509,7 @@ template <int S>
 static size_t feat3_smem_bytes() {
     constexpr int P = S + 2;
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;
-    return (size_t)2 * INH * 2 + (size_t)6 * S * 4;
+    return (size_t)2 * StreamCfg<S>::WPC * INH * 2 + (size_t)StreamCfg<S>::WPC * 6 * S * 4;
 }
 
 static size_t feat2_smem_bytes(int S, int R) {
