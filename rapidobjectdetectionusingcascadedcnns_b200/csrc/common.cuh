@@ -47,12 +47,19 @@ struct rodc_plan {
     std::vector<rodc::LevelInfo> levels;
     std::vector<int32_t> win_level, win_x, win_y, norm;       // norm: [N*4]
     std::vector<int32_t> tables;                               // bounds + coefficients of all levels
+    // horizontal pass, dp4a form: one item per (level, output x): [word0, n_words, coef word, out byte, level w, 0,0,0]
+    // and per source word 4 packed coefficient limbs (c0 | c1 | c2 | pad), see plan.cu
+    std::vector<int32_t> hitems;
+    std::vector<uint32_t> hcoef;
     int64_t pyramid_bytes = 0, scratch_bytes = 0;
     int fits = 1;
     // device copies (lazily uploaded on first GPU use; device of first use)
     int device = -1;
     rodc::LevelInfo* d_levels = nullptr;
     int32_t* d_tables = nullptr;
+    int32_t* d_hitems = nullptr;
+    uint32_t* d_hcoef = nullptr;
+    int n_hitems = 0;
     int32_t* d_win = nullptr;          // [N, 8]: level, x, y, level_w, norm[4] -- see plan.cu
     int32_t* d_row_start = nullptr;    // [n_levels+1] prefix of level heights (vertical-pass grid)
     int total_rows = 0;

@@ -123,6 +123,26 @@ extern "C" int rodc_plan_create(int img_w, int img_h, int win, double factor, do
                 lv.kx = ks;
                 lv.hx_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
                 lv.hx_coef = (int64_t)p->tables.size();   p->tables.insert(p->tables.end(), c.begin(), c.end());
+                // dp4a form of the same coefficients: taps grouped in aligned source words of 4 pixels, every
+                // 22-bit coefficient split into three u8 limbs (exact integer arithmetic: sum = a0 + a1<<8 + a2<<16)
+                for (int xx = 0; xx < lv.w; ++xx) {
+                    const int xmin = b[2 * xx], cnt = b[2 * xx + 1];
+                    const int word0 = xmin >> 2, nw = ((xmin + cnt + 3) >> 2) - word0;
+                    p->hitems.push_back(word0); p->hitems.push_back(nw);
+                    p->hitems.push_back((int32_t)(p->hcoef.size() / 4));
+                    p->hitems.push_back((int32_t)(lv.scratch_off + (int64_t)xx * 3));   // + y * w * 3 in the kernel
+                    p->hitems.push_back(lv.w);
+                    p->hitems.push_back(0); p->hitems.push_back(0); p->hitems.push_back(0);
+                    for (int wi = 0; wi < nw; ++wi) {
+                        uint32_t limb[3] = {0u, 0u, 0u};
+                        for (int q = 0; q < 4; ++q) {
+                            const int x = (word0 + wi) * 4 + q, tap = x - xmin;
+                            const uint32_t cf = (tap >= 0 && tap < cnt) ? (uint32_t)c[(size_t)xx * ks + tap] : 0u;
+                            for (int l = 0; l < 3; ++l) limb[l] |= ((cf >> (8 * l)) & 0xffu) << (8 * q);
+                        }
+                        p->hcoef.push_back(limb[0]); p->hcoef.push_back(limb[1]); p->hcoef.push_back(limb[2]); p->hcoef.push_back(0u);
+                    }
+                }
                 rodc::pillow_coeffs(img_h, lv.h, b, c, ks);
                 lv.ky = ks;
                 lv.vy_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
@@ -142,6 +162,8 @@ extern "C" int rodc_plan_create(int img_w, int img_h, int win, double factor, do
 rodc_plan::~rodc_plan() {
     if (d_levels) cudaFree(d_levels);
     if (d_tables) cudaFree(d_tables);
+    if (d_hitems) cudaFree(d_hitems);
+    if (d_hcoef) cudaFree(d_hcoef);
     if (d_win) cudaFree(d_win);
     if (d_row_start) cudaFree(d_row_start);
 }
@@ -157,6 +179,11 @@ int rodc_plan::ensure_device() {
     size_t nt = tables.size() ? tables.size() : 1;
     RODC_CUDA(cudaMalloc(&d_tables, nt * sizeof(int32_t)));
     if (tables.size()) RODC_CUDA(cudaMemcpy(d_tables, tables.data(), tables.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    n_hitems = (int)(hitems.size() / 8);
+    RODC_CUDA(cudaMalloc(&d_hitems, (hitems.size() ? hitems.size() : 8) * sizeof(int32_t)));
+    if (hitems.size()) RODC_CUDA(cudaMemcpy(d_hitems, hitems.data(), hitems.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    RODC_CUDA(cudaMalloc(&d_hcoef, (hcoef.size() ? hcoef.size() : 4) * sizeof(uint32_t)));
+    if (hcoef.size()) RODC_CUDA(cudaMemcpy(d_hcoef, hcoef.data(), hcoef.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     // packed window rows: [N,8] = level, x, y, level_w, norm[4]
     size_t N = win_level.size();
     std::vector<int32_t> rows((N ? N : 1) * 8, 0);
