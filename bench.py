@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
 
 A "step" is one pass of the whole path (pyramid -> 3 cascade stages with compaction and fused
-re-crop -> groupRectangles) over one batch of B synthetic 640x480 frames with random-init
+re-crop -> groupRectangles) over one batch of B (default 32) synthetic 640x480 frames with random-init
 (Xavier) weights of the reference architecture: BASELINE config 2, batched.  Prints ONE JSON line.
 
   value      frames/s with the frame batch already resident in HBM (device-timed, CUDA events)
@@ -134,9 +134,9 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=16, help="frames per step and per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="frames per step and per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fc1", default="tensor", choices=["tensor", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

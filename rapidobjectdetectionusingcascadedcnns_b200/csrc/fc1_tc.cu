@@ -236,6 +236,182 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------ 2-CTA variant (cta_group::2), optional
+// Built to test whether the L2 -> SM fill rate (96 KB per k-block and SM) limits the 1-CTA kernel; it does
+// not (see fc1_use_2cta below), so this variant is opt-in.  Here two CTAs of a cluster (one TPC pair) share every MMA: M = 256 (128 rows per CTA),
+// N = 256 with each CTA holding HALF of the B tile, so a CTA streams 64 KB per k-block instead of 96 KB
+// (A_hi, A_lo 128 x 64 + B_hi, B_lo 128 x 64) and three stages fit in shared memory.
+//   - both CTAs issue their TMA loads with .cta_group::2 onto the LEADER's full barrier (count 2)
+//   - only the leader's MMA lane issues tcgen05.mma.cta_group::2; its commits are multicast to the
+//     smem-empty and tmem-full barriers of both CTAs
+//   - both CTAs drain their own TMEM half; the peer's epilogue warps arrive remotely on the leader's
+//     tmem-empty barrier (count 2 x EPI_WARPS)
+constexpr int STAGES2 = 3;
+constexpr int BN_HALF = BN / 2;
+constexpr int B_HALF_TILE = BN_HALF * BK * 2;              // 16 KB
+constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF_TILE; // 64 KB per CTA and k-block
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
+               float out_scale) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* bar_full = bars;                       // [STAGES2]  (used on the leader only)
+    uint64_t* bar_empty = bars + STAGES2;            // [STAGES2]  per CTA
+    uint64_t* bar_tfull = bars + 2 * STAGES2;        // [2]        per CTA
+    uint64_t* bar_tempty = bars + 2 * STAGES2 + 2;   // [2]        (used on the leader only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int n_tile = pair & 1, m_pair = pair >> 1;
+    const int m0 = m_pair * (2 * BM) + (int)rank * BM;      // this CTA's 128 rows
+    const int n0 = n_tile * BN;
+    const int num_chunks = (num_kb + kc - 1) / kc;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(smem_u32(&bar_full[s]), 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_tfull[b]), 1); mbar_init(smem_u32(&bar_tempty[b]), 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                     // barrier inits + TMEM allocation visible in both CTAs
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[s]), 0);
+                if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * STAGE2_BYTES);   // both CTAs' bytes land here
+                else mbar_arrive_cluster(full_leader);
+                const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
+                tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
+                tma_load_2d_2sm(base + A_TILE, &map_a_lo, full_leader, kb * BK, m0);
+                tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
+                tma_load_2d_2sm(base + 2 * A_TILE + B_HALF_TILE, &map_b_lo, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
+                const int chunk = kb / kc, kin = kb - chunk * kc;
+                const int buf = chunk & 1;
+                if (kin == 0) mbar_wait(smem_u32(&bar_tempty[buf]), ((uint32_t)(chunk >> 1) & 1u) ^ 1u);   // drained in both CTAs
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                #pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {                // the small cross terms first
+                    const uint32_t koff = k * UMMA_K * 2;
+                    const uint64_t a_hi = smem_desc_sw128(base + koff);
+                    const uint64_t a_lo = smem_desc_sw128(base + A_TILE + koff);
+                    const uint64_t b_hi = smem_desc_sw128(base + 2 * A_TILE + koff);
+                    const uint64_t b_lo = smem_desc_sw128(base + 2 * A_TILE + B_HALF_TILE + koff);
+                    umma_f16_2sm(acc, a_hi, b_lo, IDESC2, (kin | k) != 0);
+                    umma_f16_2sm(acc, a_lo, b_hi, IDESC2, 1u);
+                }
+                #pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {                // then the dominant hi*hi terms
+                    const uint32_t koff = k * UMMA_K * 2;
+                    umma_f16_2sm(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), IDESC2, 1u);
+                }
+                umma_commit_2sm(smem_u32(&bar_empty[s]));              // smem slots of BOTH CTAs free
+                if (kin == kc - 1 || kb == num_kb - 1) umma_commit_2sm(smem_u32(&bar_tfull[buf]));
+            }
+        }
+    } else {
+        const int q = warp & 3, hcol = (warp - 2) >> 2;
+        float acc[128];
+        #pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(chunk >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hcol * 128);
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bar_tempty[buf]), 0));
+        }
+        const int row = m0 + q * 32 + lane;
+        if (row < m) {
+            float* orow = out + (int64_t)row * ld_out + n0 + hcol * 128;
+            const float* brow = bias + n0 + hcol * 128;
+            #pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+                float4 o;
+                o.x = fmaxf(fmaf(acc[j + 0], out_scale, __ldg(brow + j + 0)), 0.f);
+                o.y = fmaxf(fmaf(acc[j + 1], out_scale, __ldg(brow + j + 1)), 0.f);
+                o.z = fmaxf(fmaf(acc[j + 2], out_scale, __ldg(brow + j + 2)), 0.f);
+                o.w = fmaxf(fmaf(acc[j + 3], out_scale, __ldg(brow + j + 3)), 0.f);
+                *reinterpret_cast<float4*>(orow + j) = o;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                     // nobody exits while the pair still uses its smem / TMEM
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -277,6 +453,15 @@ static int fc1_chunk_kblocks() {
     return kc;
 }
 
+// RODC_FC1_2CTA=1 selects the cta_group::2 kernel.  Measured on B200 inside the bench step it is 2-4 %
+// SLOWER than the single-CTA kernel (564 vs 579 frames/s): the step runs under sw_power_cap (SM clock
+// ~1.77 GHz), so fc1 is limited by power, not by the L2 -> SM fill rate the pair was meant to relieve.
+static bool fc1_use_2cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RODC_FC1_2CTA"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 }  // namespace tc
 
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
@@ -289,6 +474,17 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
     RODC_CHECK_ARG((reinterpret_cast<uintptr_t>(bott) & 15) == 0, "bottleneck buffer must be 16-byte aligned");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
+    const float out_scale2 = ldexpf(1.f, -(s->a_exp + s->w_exp));
+    if (fc1_use_2cta()) {
+        if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
+            (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN_HALF)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN_HALF))) return rc;
+        RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * 2u;      // (M pairs) x (2 N tiles)
+        fc1_tc2_kernel<<<pairs * 2u, THREADS, SMEM2_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
+                                                                 (int)(s->K / BK), fc1_chunk_kblocks(), out_scale2);
+        RODC_LAUNCH_CHECK();
+        return RODC_OK;
+    }
     if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
         (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN))) return rc;
     RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
