@@ -67,9 +67,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -79,7 +79,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.1)]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -217,16 +218,19 @@ def main():
         out = app.run_inference_on_images(infos, merge=True)
         last["out"] = out
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                    # started early: nvidia-smi takes a while to come up
     for _ in range(warmup):
         step_resident()
     barrier()
     L = _lib.lib()
     L.rodc_profile_enable(1)
     eng.kernel_launches = 0
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_begin = time.time()
     ms_total = timed(step_resident, args.steps)
-    clocks = sampler.stop()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = eng.kernel_launches
     import ctypes as C
     fc1_ms, fc1_fl, fc1_n = C.c_double(), C.c_double(), C.c_int64()
