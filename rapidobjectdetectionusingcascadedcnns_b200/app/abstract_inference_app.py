@@ -35,6 +35,21 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         """Whole path for a list of same-size host frames; one result list per frame."""
         return
 
+    def _extract_windows(self, img, convert_raw_to_np=True):
+        """`:158-183`: wrapper of ``Window.extract_windows`` that swallows per-image errors (-> ``([], [])``)."""
+        try:
+            windows_raw, windows_info = Window.extract_windows(img, convert_raw_to_np)
+            if len(windows_raw) < 1:
+                raise ValueError("Could not extract any windows from the given image")
+            return windows_raw, windows_info
+        except FileNotFoundError:
+            log.log(" .. Skipped {}, because the file could not be found".format(getattr(img, "path_resized", img)))
+            return [], []
+        except Exception:
+            log.log(" .. Skipped {}, because of an unexpected error:\n{}".format(getattr(img, "path_resized", img),
+                                                                               traceback.format_exc()))
+            return [], []
+
     def _load_frame(self, img):
         """Decode/fetch one image; errors are swallowed like `:165-183` (image yields [])."""
         try:

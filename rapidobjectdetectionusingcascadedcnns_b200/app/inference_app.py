@@ -58,8 +58,26 @@ class InferenceApp(AbstractInferenceApp):
             self._models = [StageModel.load(p) for p in self._stage_files()]
         return self._models
 
+    @staticmethod
+    def _check_supported_config():
+        """Options of the reference that this path does not implement fail loudly instead of being ignored."""
+        if not cf.get("cascade_scale_patches_individually") or cf.get("cascade_scale_patches_individually_iff_not_cached"):
+            raise NotImplementedError("only cascade_scale_patches_individually=True (crop + cv2.resize per survivor, the "
+                                      "reference default, inference_cascade_app.py:363-373) is implemented")
+        if cf.get("append_inception"):
+            raise NotImplementedError("the Inception splice needs a network download and is out of scope")
+        if cf.get("conv_stride") != 1 or cf.get("pooling_stride") != 1 or cf.get("pooling_size") != 3 or \
+                cf.get("conv_filter_size") != 3 or list(cf.get("conv_filter_sizes")) != [32]:
+            raise NotImplementedError("only the default stage architecture (one 3x3x32 conv, stride 1, 3x3/1 max-pool) is built")
+
+    def _extract_windows(self, img, convert_raw_to_np=True):
+        """`:297-300`: the window size comes from the loaded model, then the common extraction."""
+        self._update_input_dims()
+        return super()._extract_windows(img, convert_raw_to_np)
+
     def _init_tf(self):
         """Load the stage model(s) and create the device engine (replaces `:93-115`)."""
+        self._check_supported_config()
         if not self._tf_initialized:
             from ..engine import CascadeEngine
             models = self._load_models()

@@ -138,6 +138,32 @@ class Window(Rectangle):
     def height_norm(self):
         return int(self.ymax_norm - self.ymin_norm)
 
+    @classmethod
+    def extract_windows(cls, img, convert_raw_to_np=True):
+        """All sliding windows of ``img`` (`data/rectangles.py:309-435`): returns ``(windows_raw,
+        windows_info)`` in the reference's order (level, x outer, y inner) with ``cf img_width`` as the
+        window size.  The pyramid and the crops come from the GPU (librodc planner + K1 + window gather,
+        bit-exact with the reference's Pillow path); raises ValueError like ``Window.raw`` when a window
+        leaves its level."""
+        import torch
+        from .. import config as cf
+        from .. import native
+        frame = img.raw_original(True)
+        win = int(cf.get("img_width"))
+        plan = native.Plan(frame.shape[1], frame.shape[0], win, float(cf.get("window_scale_factor")),
+                           float(cf.get("min_window_length")))
+        if plan.n_windows and not plan.fits:
+            raise ValueError("xmax must not leave the image boundaries")
+        infos = [cls(int(x), int(y), int(x) + win, int(y) + win, img, float(plan.scale[l]))
+                 for l, x, y in zip(plan.win_level.tolist(), plan.win_x.tolist(), plan.win_y.tolist())]
+        if plan.n_windows:
+            d = torch.from_numpy(frame[None].copy()).cuda()
+            raw = native.extract_windows(plan, native.pyramid(plan, d)).cpu().numpy()
+        else:
+            import numpy as np
+            raw = np.zeros((0, win, win, 3), np.uint8)
+        return (raw if convert_raw_to_np else list(raw)), infos
+
     @property
     def raw_norm(self):
         """Unscaled pixels of the receptive field in the original frame (`:293-307`)."""

@@ -212,3 +212,25 @@ def test_non_default_stage_sizes_use_generic_kernel(pkg):
         assert np.abs(lg - st.logits).max() <= 1e-3 * np.abs(st.logits).max()
         assert np.array_equal(res.trace["keep"][i].cpu().numpy(), st.keep_idx)
     assert np.array_equal(g, ref)
+
+
+def test_extract_windows_entry_points(pkg):
+    """``Window.extract_windows`` / ``app._extract_windows`` return the reference's windows and infos."""
+    import hashlib
+    g, frames, weights, _ = case_inputs("cascade_small")
+    _set_cf(pkg, g["meta"]["cf"])
+    app = pkg.InferenceCascadeApp("x", stage_models=[pkg.StageModel(w) for w in weights])
+    raws, rows, scales = [], [], []
+    for fi, fr in enumerate(frames):
+        raw, infos = app._extract_windows(pkg.ArrayImageInfo(fr, "e%d.png" % fi))
+        raws.append(raw)
+        rows += [[fi, w.xmin, w.ymin, w.xmin_norm, w.ymin_norm, w.xmax_norm, w.ymax_norm] for w in infos]
+        scales += [w.scale for w in infos]
+        assert raw.dtype == np.uint8 and raw.shape[1:] == (12, 12, 3) and len(infos) == raw.shape[0]
+    assert hashlib.sha256(np.concatenate(raws).tobytes()).hexdigest() == str(g["windows_raw_sha"])
+    assert np.array_equal(np.asarray(rows, np.int32), g["win_table"])
+    assert np.array_equal(np.asarray(scales), g["win_scale"])
+    assert app._extract_windows(pkg.ArrayImageInfo(np.zeros((6, 6, 3), np.uint8), "tiny.png")) == ([], [])
+    pkg.cf.set("cascade_scale_patches_individually", False)
+    with pytest.raises(NotImplementedError):
+        pkg.InferenceCascadeApp("y", stage_models=[pkg.StageModel(w) for w in weights]).run_inference_on_images([])
