@@ -299,7 +299,8 @@ def _run_prefix(frames, ws, cfg, upto: int, arith: str) -> np.ndarray:
     raw = np.concatenate(raws); norm = np.concatenate(norms); image = np.concatenate(ids)
     bott = None
     for i in range(upto + 1):
-        probs, b, logits = stage_net.stage_forward_batched(raw, ws[i], bott if i > 0 else None, dtype=torch.float64)
+        probs, b, logits = stage_net.stage_forward_batched(raw, ws[i], bott if (i > 0 and sub.reuse_bottlenecks) else None,
+                                                           dtype=torch.float64)
         if i == upto:
             return logits.numpy()
         keep = np.nonzero(probs[:, 1].numpy() > _threshold(sub, i, n))[0]

@@ -234,3 +234,27 @@ def test_extract_windows_entry_points(pkg):
     pkg.cf.set("cascade_scale_patches_individually", False)
     with pytest.raises(NotImplementedError):
         pkg.InferenceCascadeApp("y", stage_models=[pkg.StageModel(w) for w in weights]).run_inference_on_images([])
+
+
+def test_no_bottleneck_reuse_and_launch_chunking(pkg):
+    """reuse_bottlenecks=False (fc2 sees only its own 512 features) and a tiny max_windows_per_launch that
+    cuts the same-shape group into several launches: same boxes as the fp64 oracle."""
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    pkg.cf.set("min_window_length", 0.2)
+    pkg.cf.set("reuse_bottlenecks", False)
+    ocfg = oc.Config(min_window_length=0.2, reuse_bottlenecks=False)
+    base = synth.xavier_cascade(reuse_bottlenecks=False)
+    assert [w["fc2_W"].shape[0] for w in base] == [512, 512, 512]
+    frames = [synth.synth_frame(120, 160, 30 + j) for j in range(5)]
+    offsets = oc.calibrate_offsets(frames[:1], base, ocfg, [0.4, 0.5, 0.5])
+    weights = synth.xavier_cascade(fg_bias_offsets=offsets, reuse_bottlenecks=False)
+    app = pkg.InferenceCascadeApp("nb", stage_models=[pkg.StageModel(w) for w in weights])
+    infos = [pkg.ArrayImageInfo(f, "nb%d.png" % i) for i, f in enumerate(frames)]
+    pkg.cf.set("max_windows_per_launch", 1500)                 # 712 windows per frame -> 2 frames per launch
+    got = app.run_inference_on_images(infos, merge=True)
+    g = np.asarray([[i, b.xmin, b.ymin, b.xmax, b.ymax, b.confidence] for i, per in enumerate(got) for b in per],
+                   np.float64).reshape(-1, 6)
+    r = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64)
+    ref = np.column_stack([r.image, r.boxes, r.conf]).astype(np.float64).reshape(-1, 6)
+    assert np.array_equal(g, ref)
