@@ -132,18 +132,26 @@ extern "C" int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, u
     const int nl = (int)p->levels.size();
     bool any_resample = false;
     for (auto& l : p->levels) any_resample |= !l.identity;
-    if (any_resample) {
-        size_t smem = (size_t)3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4);
-        if (smem > 48 * 1024) RODC_CUDA(cudaFuncSetAttribute(pyr_hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(p->img_h, n_frames);
-        pyr_hpass_kernel<<<grid, 256, smem, st>>>(frames, p->img_h, p->img_w, p->d_hitems, p->n_hitems,
-                                                   reinterpret_cast<const uint4*>(p->d_hcoef), scratch, p->scratch_bytes);
+    const size_t smem = (size_t)3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4);
+    if (any_resample && smem > 48 * 1024)
+        RODC_CUDA(cudaFuncSetAttribute(pyr_hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t frame_bytes = (int64_t)p->img_h * p->img_w * 3;
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {              // gridDim.y limit
+        const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+        const uint8_t* fr = frames + (int64_t)f0 * frame_bytes;
+        uint8_t* sc = scratch + (int64_t)f0 * p->scratch_bytes;
+        uint8_t* py = pyramid + (int64_t)f0 * p->pyramid_bytes;
+        if (any_resample) {
+            dim3 grid(p->img_h, nf);
+            pyr_hpass_kernel<<<grid, 256, smem, st>>>(fr, p->img_h, p->img_w, p->d_hitems, p->n_hitems,
+                                                       reinterpret_cast<const uint4*>(p->d_hcoef), sc, p->scratch_bytes);
+            RODC_LAUNCH_CHECK();
+        }
+        dim3 grid(p->total_rows, nf);
+        pyr_vpass_kernel<<<grid, 128, 0, st>>>(fr, p->img_h, p->img_w, p->d_levels, nl, p->d_tables, p->d_row_start,
+                                                sc, p->scratch_bytes, py, p->pyramid_bytes);
         RODC_LAUNCH_CHECK();
     }
-    dim3 grid(p->total_rows, n_frames);
-    pyr_vpass_kernel<<<grid, 128, 0, st>>>(frames, p->img_h, p->img_w, p->d_levels, nl, p->d_tables, p->d_row_start,
-                                            scratch, p->scratch_bytes, pyramid, p->pyramid_bytes);
-    RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
 
