@@ -78,6 +78,13 @@ int rodc_extract_windows(rodc_plan* p, const uint8_t* pyramid, int n_frames, uin
 /* Window metadata rows (frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm):
  *   meta [n_frames * n_windows, 5] i32, frame ids start at frame_id_base */
 int rodc_window_meta(rodc_plan* p, int n_frames, int frame_id_base, int32_t* meta, void* stream);
+/* GATHER rows of the same windows: byte offset (pyramid_base_off + frame * pyramid_bytes + level offset +
+ * (y * level_w + x) * 3) and row pitch (level_w * 3), so that windows of several frame shapes
+ * (several plans, several pyramids in one buffer) can share one stage launch -- the reference's merge
+ * mode concatenates the windows of all images the same way (abstract_inference_app.py:66-81).
+ *   win_off [n_frames * n_windows] i64, win_pitch [n_frames * n_windows] i32 */
+int rodc_window_gather_rows(rodc_plan* p, int n_frames, int64_t pyramid_base_off, int64_t* win_off,
+                            int32_t* win_pitch, void* stream);
 
 /* ---------------------------------------------------------------- K4 recrop
  * Replaces _get_increased_raw_window_for_next_net (inference_cascade_app.py:363-373):
@@ -103,6 +110,8 @@ void rodc_stage_destroy(rodc_stage* s);
 #define RODC_SRC_DENSE   0   /* windows already materialised: dense [n,S,S,3] u8            */
 #define RODC_SRC_PYRAMID 1   /* stage 0: read windows in place from the packed pyramid       */
 #define RODC_SRC_RECROP  2   /* stages >=1: crop+resize on the fly from the original frames  */
+#define RODC_SRC_GATHER  3   /* stage 0 over frames of DIFFERENT shapes: per-window byte offset + */
+                             /* row pitch into one buffer holding several packed pyramids          */
 typedef struct {
     int32_t          kind;
     const uint8_t*   dense;       /* DENSE                                                   */
@@ -112,6 +121,9 @@ typedef struct {
     const int64_t*   frame_off;
     const int32_t*   frame_hw;
     const int32_t*   meta;
+    const uint8_t*   gather_base; /* GATHER: window w starts at gather_base + win_off[w],    */
+    const int64_t*   win_off;     /*         rows are win_pitch[w] bytes apart               */
+    const int32_t*   win_pitch;
 } rodc_window_source;
 
 #define RODC_IMPL_TENSOR 0   /* tcgen05 split-fp16 GEMM (3 MMAs, fp32-grade)                 */

@@ -1,0 +1,75 @@
+"""Throughput of the other BASELINE.json configurations on one B200 (device-timed, frames resident).
+
+config 3  FDDB-shaped: 70 frames, W = 450 - 10 (j mod 5), H = 400 - 8 (j mod 7) (35 shapes), defaults
+config 4  1920x1080 stream, factor 1.2, min_window_length 0.0125 (93 645 windows / frame), 8 frames
+config 5  3840x2160, factor 1.1, min_window_length 0.0125 (161 969 windows / frame), stage-1 offset for
+          > 99.9 % rejection, 4 frames
+Random Xavier weights; configs 3/4 use calibrated fc2 offsets for ~15 % / 3 % stage-1 pass rates (random-init
+cascades otherwise pass ~99 %), config 2 (the bench) runs uncalibrated.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rapidobjectdetectionusingcascadedcnns_b200 as pkg  # noqa: E402
+from rapidobjectdetectionusingcascadedcnns_b200 import synth  # noqa: E402
+from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine  # noqa: E402
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, out
+
+
+def main():
+    rows = []
+    # ---- config 3
+    pkg.cf.reset()
+    eng = CascadeEngine(synth.xavier_cascade(fg_bias_offsets=[-40.0, -85.0, -24.0]))
+    groups = {}
+    for j in range(70):
+        h, w = synth.fddb_shape(j)
+        groups.setdefault((h, w), []).append(synth.synth_frame(h, w, 100 + j))
+    dev = {k: torch.from_numpy(np.stack(v)).cuda() for k, v in groups.items()}
+
+    def run3():
+        res = [eng.run_frames(d) for d in dev.values()]
+        return sum(r.n_windows for r in res), [sum(x) for x in zip(*[r.stage_kept for r in res])]
+    ms, (nwin, kept) = timed(run3)
+    rows.append({"config": 3, "frames": 70, "shapes": len(dev), "windows": nwin, "kept": kept, "ms": ms,
+                 "frames_per_s": 70 / ms * 1e3, "windows_per_s": nwin / ms * 1e3})
+    # ---- config 4
+    pkg.cf.reset(); pkg.cf.set("window_scale_factor", 1.2); pkg.cf.set("min_window_length", 0.0125)
+    eng = CascadeEngine(synth.xavier_cascade(fg_bias_offsets=[-60.0, -85.0, -24.0]))
+    d = torch.from_numpy(np.stack([synth.synth_frame(1080, 1920, 5000 + j) for j in range(8)])).cuda()
+    ms, res = timed(lambda: eng.run_frames(d))
+    rows.append({"config": 4, "frames": 8, "windows": res.n_windows, "kept": res.stage_kept, "ms": ms,
+                 "frames_per_s": 8 / ms * 1e3, "windows_per_s": res.n_windows / ms * 1e3})
+    # ---- config 5
+    pkg.cf.reset(); pkg.cf.set("min_window_length", 0.0125)
+    d = torch.from_numpy(np.stack([synth.synth_frame(2160, 3840, 9000 + j) for j in range(4)])).cuda()
+    pkg.cf.set("foreground_confidence_threshold", [2.0, 0.5, 0.5])
+    lg = CascadeEngine(synth.xavier_cascade()).run_frames(d, keep_trace=True).trace["logits"][0].cpu().numpy()
+    pkg.cf.set("foreground_confidence_threshold", 0.5)
+    off0 = -round(float(np.quantile(lg[:, 1] - lg[:, 0], 1 - 0.0005)) * 64) / 64
+    eng = CascadeEngine(synth.xavier_cascade(fg_bias_offsets=[off0, -85.0, -24.0]))
+    ms, res = timed(lambda: eng.run_frames(d))
+    rows.append({"config": 5, "frames": 4, "windows": res.n_windows, "kept": res.stage_kept, "ms": ms,
+                 "frames_per_s": 4 / ms * 1e3, "windows_per_s": res.n_windows / ms * 1e3})
+    print(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    main()

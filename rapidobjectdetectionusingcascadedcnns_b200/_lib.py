@@ -23,10 +23,11 @@ vp = C.c_void_p
 class WindowSource(C.Structure):
     """``rodc_window_source`` (include/rodc.h)."""
     _fields_ = [("kind", C.c_int32), ("dense", vp), ("plan", vp), ("pyramid", vp),
-                ("frames_base", vp), ("frame_off", vp), ("frame_hw", vp), ("meta", vp)]
+                ("frames_base", vp), ("frame_off", vp), ("frame_hw", vp), ("meta", vp),
+                ("gather_base", vp), ("win_off", vp), ("win_pitch", vp)]
 
 
-SRC_DENSE, SRC_PYRAMID, SRC_RECROP = 0, 1, 2
+SRC_DENSE, SRC_PYRAMID, SRC_RECROP, SRC_GATHER = 0, 1, 2, 3
 IMPL_TENSOR, IMPL_SIMT = 0, 1
 
 # name -> (restype, argtypes); every symbol include/rodc.h declares
@@ -46,6 +47,7 @@ SIGNATURES = {
     "rodc_pyramid": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
     "rodc_extract_windows": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "rodc_window_meta": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "rodc_window_gather_rows": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp]),
     "rodc_recrop": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]),
     "rodc_stage_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "rodc_stage_destroy": (None, [vp]),

@@ -32,7 +32,7 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
 
     @abc.abstractmethod
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
-        """Whole path for a list of same-size host frames; one result list per frame."""
+        """Whole path for a list of host frames (any mix of shapes); one result list per frame."""
         return
 
     def _extract_windows(self, img, convert_raw_to_np=True):
@@ -74,24 +74,35 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         if merge:
             timer_extracting = TimeWatcher("extract windows from all images and merge them")
             log.log(" -> extract")
-            groups = {}
-            usable = 0
+            usable = []                                       # (input index, image, frame) with at least one window
             for idx, img in enumerate(images):
                 arr = self._load_frame(img)
                 if arr is None:
                     continue
-                groups.setdefault(arr.shape, []).append((idx, img, arr))
-            timer_extracting.stop()
-            for shape, items in groups.items():
                 try:
-                    per_frame = self._run_group(items)
+                    n_win = self._windows_per_frame(arr.shape[1], arr.shape[0])      # raises if a window leaves its level
+                    if n_win < 1:
+                        raise ValueError("Could not extract any windows from the given image")
                 except ValueError as e:
-                    # no window fits this frame shape: every image of the group is skipped (`:165-183`)
-                    log.log(" .. Skipped {} image(s) of shape {}: {}".format(len(items), shape, e))
+                    log.log(" .. Skipped {}: {}".format(getattr(img, "path_resized", img), e))   # `:165-183`
                     continue
-                usable += len(items)
-                for (idx, _, _), boxes in zip(items, per_frame):
+                usable.append((idx, img, arr, n_win))
+            timer_extracting.stop()
+            # cut into launches of at most cf['max_windows_per_launch'] stage-0 windows, input order kept
+            budget = int(cf.get("max_windows_per_launch"))
+            chunk, acc = [], 0
+            chunks = []
+            for item in usable:
+                if chunk and acc + item[3] > budget:
+                    chunks.append(chunk); chunk, acc = [], 0
+                chunk.append(item); acc += item[3]
+            if chunk:
+                chunks.append(chunk)
+            for chunk in chunks:
+                per_frame = self._run_on_frame_batch([i for _, i, _, _ in chunk], [a for _, _, a, _ in chunk])
+                for (idx, _, _, _), boxes in zip(chunk, per_frame):
                     all_results[idx] = boxes
+            usable = len(usable)
             if usable == 0:
                 raise ValueError("Could not extract any windows from the given image")
         else:
@@ -120,17 +131,6 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         log.log("Runtime inference including window extraction: {} images in {} (avg: {}).".format(
             len(images), TimeWatcher.seconds_to_str(t_all), TimeWatcher.seconds_to_str(t_all / n)))
         return all_results
-
-    def _run_group(self, items) -> List[List[LabeledBoundingBox]]:
-        """Cut a same-shape group into launches of at most cf['max_windows_per_launch'] windows."""
-        h, w = items[0][2].shape[:2]
-        per_frame = max(1, self._windows_per_frame(w, h))
-        step = max(1, int(cf.get("max_windows_per_launch")) // per_frame)
-        out = []
-        for s in range(0, len(items), step):
-            chunk = items[s:s + step]
-            out.extend(self._run_on_frame_batch([i for _, i, _ in chunk], [a for _, _, a in chunk]))
-        return out
 
     @abc.abstractmethod
     def _windows_per_frame(self, w: int, h: int) -> int:

@@ -110,7 +110,11 @@ class InferenceApp(AbstractInferenceApp):
 
     def _windows_per_frame(self, w: int, h: int) -> int:
         self._init_tf()
-        return self._engine.plan_for(w, h).n_windows
+        self._update_input_dims()
+        plan = self._engine.plan_for(w, h)
+        if plan.n_windows and not plan.fits:
+            raise ValueError("xmax/ymax must not leave the image boundaries")          # `data/rectangles.py:286-289`
+        return plan.n_windows
 
     # ------------------------------------------------------------------ results
     @staticmethod
@@ -134,9 +138,18 @@ class InferenceApp(AbstractInferenceApp):
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
         self._init_tf()
         self._update_input_dims()
-        res = self._engine.run_frames(self._engine.stage_host_frames(frames))
+        if len({f.shape for f in frames}) == 1:
+            res = self._engine.run_frames(self._engine.stage_host_frames(frames))
+            self._log_stage_stats(res)
+            return self._boxes_from_result(res, infos, len(infos))
+        # several shapes: one merged set of stage launches (internal frame ids are grouped by shape)
+        res, order = self._engine.run_mixed(frames)
         self._log_stage_stats(res)
-        return self._boxes_from_result(res, infos, len(infos))
+        per_internal = self._boxes_from_result(res, [infos[i] for i in order], len(infos))
+        out = [[] for _ in infos]
+        for internal, i in enumerate(order):
+            out[i] = per_internal[internal]
+        return out
 
     @staticmethod
     def _log_stage_stats(res):

@@ -191,6 +191,7 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
         } else {
             const uint8_t* p; int pitch;
             if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+            else if (src.kind == RODC_SRC_GATHER) { p = src.gather_base + src.win_off[w]; pitch = src.win_pitch[w]; }
             else {
                 const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
                 const int32_t* wr = src.win + j * 8;
@@ -382,6 +383,7 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
             } else {
                 const uint8_t* p; int pitch;
                 if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+                else if (src.kind == RODC_SRC_GATHER) { p = src.gather_base + src.win_off[w]; pitch = src.win_pitch[w]; }
                 else {
                     const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
                     const int32_t* wr = src.win + j * 8;
@@ -542,6 +544,9 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     } else if (src->kind == RODC_SRC_RECROP) {
         RODC_CHECK_ARG(src->frames_base && src->frame_off && src->frame_hw && src->meta, "recrop window source incomplete");
         d.frames_base = src->frames_base; d.frame_off = src->frame_off; d.frame_hw = src->frame_hw; d.meta = src->meta;
+    } else if (src->kind == RODC_SRC_GATHER) {
+        RODC_CHECK_ARG(src->gather_base && src->win_off && src->win_pitch, "gather window source incomplete");
+        d.gather_base = src->gather_base; d.win_off = src->win_off; d.win_pitch = src->win_pitch;
     } else {
         set_error("unknown window source kind %d", src->kind);
         return RODC_ERR_ARG;

@@ -118,6 +118,18 @@ __global__ void window_meta_kernel(const int32_t* __restrict__ win, int64_t n_wi
     }
 }
 
+__global__ void window_gather_rows_kernel(const int32_t* __restrict__ win, const LevelInfo* __restrict__ levels,
+                                          int64_t n_windows, int64_t total, int64_t base_off, int64_t pyramid_bytes,
+                                          int64_t* __restrict__ win_off, int32_t* __restrict__ win_pitch) {
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = w / n_windows; const int64_t j = w - f * n_windows;
+        const int32_t* wr = win + j * 8;
+        const LevelInfo& lv = levels[wr[0]];
+        win_off[w] = base_off + f * pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+        win_pitch[w] = lv.w * 3;
+    }
+}
+
 }  // namespace rodc
 
 using namespace rodc;
@@ -176,6 +188,21 @@ extern "C" int rodc_window_meta(rodc_plan* p, int n_frames, int frame_id_base, i
     const int64_t total = N * n_frames;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
     window_meta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, N, total, frame_id_base, meta);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+extern "C" int rodc_window_gather_rows(rodc_plan* p, int n_frames, int64_t pyramid_base_off, int64_t* win_off,
+                                       int32_t* win_pitch, void* stream) {
+    RODC_CHECK_ARG(p && win_off && win_pitch, "rodc_window_gather_rows: NULL argument");
+    const int64_t N = (int64_t)p->win_level.size();
+    if (n_frames <= 0 || N == 0) return RODC_OK;
+    RODC_CHECK_ARG(p->fits, "rodc_window_gather_rows: a window leaves its level (the reference raises ValueError and skips the image)");
+    int rc = p->ensure_device(); if (rc) return rc;
+    const int64_t total = N * n_frames;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    window_gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, p->d_levels, N, total, pyramid_base_off,
+                                                                     p->pyramid_bytes, win_off, win_pitch);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

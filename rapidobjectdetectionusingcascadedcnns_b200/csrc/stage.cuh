@@ -35,6 +35,7 @@ struct SrcDev {
     const uint8_t* dense;
     const uint8_t* pyramid; int64_t pyramid_bytes; const LevelInfo* levels; const int32_t* win; int64_t n_windows;
     const uint8_t* frames_base; const int64_t* frame_off; const int32_t* frame_hw; const int32_t* meta;
+    const uint8_t* gather_base; const int64_t* win_off; const int32_t* win_pitch;
 };
 
 int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out);

@@ -211,6 +211,63 @@ class CascadeEngine:
             src0 = native.make_source(plan=plan, pyr=pyr)
             return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace)
 
+    def run_mixed(self, frames: Sequence[np.ndarray], keep_trace: bool = False) -> Tuple[GroupResult, List[int]]:
+        """Whole path for host frames of DIFFERENT shapes in one set of stage launches (the reference's
+        merge mode concatenates the windows of all images, `app/abstract_inference_app.py:66-81`).
+        One K1 launch pair per shape writes into a shared pyramid buffer; stage 0 reads its windows
+        through a per-window (offset, pitch) table, later stages re-crop from a table of all frames.
+        Returns the result with INTERNAL frame ids (grouped by shape) and ``order``: internal id -> index
+        into ``frames``.  Every frame must yield windows (callers filter with ``plan_for``)."""
+        with torch.cuda.device(self.device):
+            groups: Dict[Tuple[int, int], List[int]] = {}
+            for i, f in enumerate(frames):
+                groups.setdefault((f.shape[0], f.shape[1]), []).append(i)
+            order = [i for idx in groups.values() for i in idx]
+            plans = {k: self.plan_for(k[1], k[0]) for k in groups}
+            for k, p in plans.items():
+                if p.n_windows < 1:
+                    raise ValueError("Could not extract any windows from the given image")
+                if not p.fits:
+                    raise ValueError("xmax/ymax must not leave the image boundaries")
+            # one pinned buffer with all frames (group order) -> one H2D copy
+            sizes = [frames[i].size for i in order]
+            total = int(sum(sizes))
+            buf = getattr(self, "_pinned", None)
+            if buf is None or buf.numel() < total:
+                buf = torch.empty((total,), dtype=torch.uint8).pin_memory()
+                self._pinned = buf
+            host = buf[:total].numpy()
+            offs, o = [], 0
+            for i, sz in zip(order, sizes):
+                host[o:o + sz] = frames[i].reshape(-1)
+                offs.append(o); o += sz
+            flat = buf[:total].to(self.device, non_blocking=True)
+            table = native.FrameTable(flat, offs, [(frames[i].shape[0], frames[i].shape[1]) for i in order])
+            n_windows = sum(len(idx) * plans[k].n_windows for k, idx in groups.items())
+            pyr_bytes = sum(len(idx) * plans[k].pyramid_bytes for k, idx in groups.items())
+            pyr = torch.empty((pyr_bytes,), dtype=torch.uint8, device=self.device)
+            win_off = torch.empty((n_windows,), dtype=torch.int64, device=self.device)
+            win_pitch = torch.empty((n_windows,), dtype=torch.int32, device=self.device)
+            meta0 = torch.empty((n_windows, 5), dtype=torch.int32, device=self.device)
+            fbase = wbase = pbase = 0
+            pos = 0
+            for k, idx in groups.items():
+                p, n = plans[k], len(idx)
+                fsz = k[0] * k[1] * 3
+                d = flat[offs[pos]:offs[pos] + n * fsz].view(n, k[0], k[1], 3)
+                native.pyramid(p, d, out=pyr[pbase:pbase + n * p.pyramid_bytes].view(n, p.pyramid_bytes))
+                nw = n * p.n_windows
+                native.window_gather_rows(p, n, pbase, win_off[wbase:wbase + nw], win_pitch[wbase:wbase + nw])
+                from . import _lib as _l
+                import ctypes as C
+                _l.check(_l.lib().rodc_window_meta(p.handle, n, fbase, C.c_void_p(meta0[wbase:wbase + nw].data_ptr()),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rodc_window_meta")
+                self.kernel_launches += 4
+                fbase += n; wbase += nw; pbase += n * p.pyramid_bytes; pos += n
+            src0 = native.make_source(gather_base=pyr, win_off=win_off, win_pitch=win_pitch)
+            self._keepalive0 = (pyr, win_off, win_pitch, flat, table)
+            return self._run_stages(src0, n_windows, meta0, table, len(order), keep_trace), order
+
     def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False) -> GroupResult:
         """``run_inference_on_windows``: caller-extracted stage-0 windows ``[n,S,S,3]`` u8 plus their
         metadata rows ``(frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm)``; ``frames`` are the

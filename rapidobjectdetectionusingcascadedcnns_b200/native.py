@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_SIMT, IMPL_TENSOR, SRC_DENSE, SRC_PYRAMID, SRC_RECROP, WindowSource, check
+from ._lib import IMPL_SIMT, IMPL_TENSOR, SRC_DENSE, SRC_GATHER, SRC_PYRAMID, SRC_RECROP, WindowSource, check
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -124,6 +124,14 @@ def window_meta(plan: Plan, n_frames: int, frame_id_base: int, device) -> torch.
     return out
 
 
+def window_gather_rows(plan: Plan, n_frames: int, pyramid_base_off: int, win_off: torch.Tensor, win_pitch: torch.Tensor):
+    """Fill ``win_off`` (i64) / ``win_pitch`` (i32) slices for ``n_frames`` frames of ``plan`` whose packed pyramids
+    start ``pyramid_base_off`` bytes into the shared gather buffer."""
+    _require_cuda(win_off, win_pitch)
+    check(_lib.lib().rodc_window_gather_rows(plan.handle, int(n_frames), int(pyramid_base_off), _ptr(win_off), _ptr(win_pitch),
+                                             _stream()), "rodc_window_gather_rows")
+
+
 class FrameTable:
     """Device table of the original frames for the RECROP source: one flat u8 buffer plus
     per-frame byte offsets and (H, W)."""
@@ -206,9 +214,15 @@ class Stage:
 
 def make_source(*, dense: Optional[torch.Tensor] = None, plan: Optional[Plan] = None,
                 pyr: Optional[torch.Tensor] = None, table: Optional[FrameTable] = None,
-                meta: Optional[torch.Tensor] = None) -> WindowSource:
+                meta: Optional[torch.Tensor] = None, gather_base: Optional[torch.Tensor] = None,
+                win_off: Optional[torch.Tensor] = None, win_pitch: Optional[torch.Tensor] = None) -> WindowSource:
     s = WindowSource()
-    if dense is not None:
+    if gather_base is not None:
+        _require_cuda(gather_base, win_off, win_pitch)
+        assert win_off.dtype == torch.int64 and win_pitch.dtype == torch.int32
+        s.kind = SRC_GATHER; s.gather_base = gather_base.data_ptr(); s.win_off = win_off.data_ptr()
+        s.win_pitch = win_pitch.data_ptr()
+    elif dense is not None:
         _require_cuda(dense)
         assert dense.dtype == torch.uint8 and dense.is_contiguous()
         s.kind = SRC_DENSE; s.dense = dense.data_ptr()
