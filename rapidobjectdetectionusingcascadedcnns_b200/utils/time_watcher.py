@@ -1,30 +1,40 @@
-"""Wall-clock timers with the reference's interface (`utils/time_watcher.py:10-47`)."""
-from datetime import timedelta
-from time import time
+"""Wall-clock stopwatch used for the three runtime figures the inference apps log
+("window extraction", "inference only", "including window extraction").
 
-from . import log
+Interface-compatible with the reference's `utils/time_watcher.py` (a named watcher that starts on
+construction, ``stop()``, ``elapsed_seconds``, ``seconds_to_str``); built on ``perf_counter`` so that
+short GPU-side phases are not quantised by the system clock.
+"""
+import datetime
+import time
+
+from . import log as _log
 
 
 class TimeWatcher:
+    __slots__ = ("label", "_t0", "_elapsed")
+
     def __init__(self, name: str):
-        self._name = name
+        self.label = str(name)
+        self._elapsed = None
+        self._t0 = 0.0
         self.start()
 
-    def start(self):
-        self._start_time = time()
-        self._end_time = None
-        self._elapsed_seconds = None
-        log.log("TimeWatcher Start: {}".format(self._name))
+    def start(self) -> None:
+        _log.log("TimeWatcher Start: " + self.label)
+        self._elapsed = None
+        self._t0 = time.perf_counter()
 
-    def stop(self):
-        self._end_time = time()
-        self._elapsed_seconds = self._end_time - self._start_time
-        log.log("TimeWatcher Stop {}: {}".format(self._name, self.seconds_to_str(self._elapsed_seconds)))
+    def stop(self) -> float:
+        self._elapsed = time.perf_counter() - self._t0
+        _log.log("TimeWatcher Stop %s: %s" % (self.label, self.seconds_to_str(self._elapsed)))
+        return self._elapsed
 
     @property
     def elapsed_seconds(self):
-        return self._elapsed_seconds
+        """Seconds between ``start`` and the last ``stop`` (``None`` while running)."""
+        return self._elapsed
 
     @staticmethod
     def seconds_to_str(time_in_seconds) -> str:
-        return str(timedelta(seconds=time_in_seconds))
+        return str(datetime.timedelta(seconds=float(time_in_seconds)))
