@@ -105,6 +105,15 @@ int  rodc_stage_create(int in_size, int conv_channels, int fc1_size, int n_prev,
                        const float* conv_w, const float* conv_b,
                        const float* fc1_w, const float* fc1_b,
                        const float* fc2_w, const float* fc2_b, rodc_stage** out);
+/* General stage architecture (network/net.py:189-221): n_conv conv layers with channels[l] filters of
+ * ksize x ksize, stride conv_stride, SAME padding, each followed by ReLU and a SAME max-pool of pool_size /
+ * pool_stride; weights conv_w[l] HWIO [k,k,Cin,Cout].  The reference default (one 3x3x32 conv, 3x3/1 pool) is
+ * routed to the specialised kernels; everything else runs a generic fp32 kernel (correctness path). */
+int  rodc_stage_create_general(int in_size, int n_conv, const int32_t* channels, int ksize, int conv_stride,
+                               int pool_size, int pool_stride,
+                               const float* const* conv_w, const float* const* conv_b,
+                               int fc1_size, int n_prev, const float* fc1_w, const float* fc1_b,
+                               const float* fc2_w, const float* fc2_b, rodc_stage** out);
 void rodc_stage_destroy(rodc_stage* s);
 
 #define RODC_SRC_DENSE   0   /* windows already materialised: dense [n,S,S,3] u8            */

@@ -50,6 +50,8 @@ SIGNATURES = {
     "rodc_window_gather_rows": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp]),
     "rodc_recrop": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]),
     "rodc_stage_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "rodc_stage_create_general": (C.c_int, [C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                            C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]),
     "rodc_stage_destroy": (None, [vp]),
     "rodc_stage_workspace_bytes": (C.c_int64, [vp, C.c_int64, C.c_int]),
     "rodc_stage_forward": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, C.c_int, vp, vp,

@@ -66,9 +66,6 @@ class InferenceApp(AbstractInferenceApp):
                                       "reference default, inference_cascade_app.py:363-373) is implemented")
         if cf.get("append_inception"):
             raise NotImplementedError("the Inception splice needs a network download and is out of scope")
-        if cf.get("conv_stride") != 1 or cf.get("pooling_stride") != 1 or cf.get("pooling_size") != 3 or \
-                cf.get("conv_filter_size") != 3 or list(cf.get("conv_filter_sizes")) != [32]:
-            raise NotImplementedError("only the default stage architecture (one 3x3x32 conv, stride 1, 3x3/1 max-pool) is built")
 
     def _extract_windows(self, img, convert_raw_to_np=True):
         """`:297-300`: the window size comes from the loaded model, then the common extraction."""
@@ -81,7 +78,10 @@ class InferenceApp(AbstractInferenceApp):
         if not self._tf_initialized:
             from ..engine import CascadeEngine
             models = self._load_models()
-            self._engine = CascadeEngine([m.weights for m in models], device=self._device, single=self._single)
+            geos = [dict(in_size=m.in_size, conv_stride=m.conv_stride, pool_size=m.pool_size, pool_stride=m.pool_stride)
+                    for m in models]
+            self._engine = CascadeEngine([m.weights for m in models], device=self._device, single=self._single,
+                                         geometries=geos)
             self._tf_initialized = True
 
     def clean(self):

@@ -526,6 +526,122 @@ static int pick_rows2(int S) {
     return 4;
 }
 
+// ------------------------------------------------------------------ general architecture (correctness path)
+// Several conv layers, other filter counts, conv / pool strides (network/net.py:189-221 with the cf keys
+// conv_filter_sizes, conv_filter_size, conv_stride, pooling_size, pooling_stride; TF SAME padding:
+// out = ceil(in / s), pad_total = max((out - 1) s + k - in, 0), pad_before = pad_total / 2).  One CTA per
+// window walks the layers with fp32 FMAs on ping-pong activation maps in a global scratch slice.  The
+// reference's default net never takes this path; it exists so that the stage-model interface is complete.
+struct GenNet {
+    int n_conv, ksize, conv_stride, pool_size, pool_stride;
+    int chan[8];
+    const float* w[8];
+    const float* b[8];
+};
+
+__device__ __forceinline__ int same_out(int in, int s) { return (in + s - 1) / s; }
+__device__ __forceinline__ int same_pad_before(int in, int k, int s) {
+    const int total = max((same_out(in, s) - 1) * s + k - in, 0);
+    return total / 2;
+}
+
+template <int OUT_SPLIT>
+__global__ void __launch_bounds__(FEAT_THREADS)
+features_general_kernel(SrcDev src, int64_t first, int64_t n, int S, GenNet net, float* __restrict__ scratch, int64_t max_act,
+                        float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                        int64_t K) {
+    extern __shared__ int gtabs[];
+    float* bufA = scratch + (int64_t)blockIdx.x * 2 * max_act;
+    float* bufB = bufA + max_act;
+    const int tid = threadIdx.x;
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
+        const int64_t w = first + wrel;
+        __syncthreads();
+        // ---- input window as float [S][S][3]
+        Crop crop;
+        if (src.kind == RODC_SRC_RECROP) { crop = make_crop(src, w); fill_recrop_tables(crop, S, gtabs); }
+        __syncthreads();
+        for (int i = tid; i < S * S; i += FEAT_THREADS) {
+            const int y = i / S, x = i - y * S;
+            float p0, p1, p2;
+            if (src.kind == RODC_SRC_RECROP) {
+                int px[3];
+                recrop_pixel(crop, S, gtabs, y, x, px);
+                p0 = (float)px[0]; p1 = (float)px[1]; p2 = (float)px[2];
+            } else {
+                const uint8_t* p; int pitch;
+                if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+                else if (src.kind == RODC_SRC_GATHER) { p = src.gather_base + src.win_off[w]; pitch = src.win_pitch[w]; }
+                else {
+                    const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
+                    const int32_t* wr = src.win + j * 8;
+                    const LevelInfo& lv = src.levels[wr[0]];
+                    p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+                    pitch = lv.w * 3;
+                }
+                const uint8_t* q = p + (int64_t)y * pitch + x * 3;
+                p0 = (float)q[0]; p1 = (float)q[1]; p2 = (float)q[2];
+            }
+            bufA[i * 3 + 0] = p0; bufA[i * 3 + 1] = p1; bufA[i * 3 + 2] = p2;
+        }
+        __syncthreads();
+        int H = S, cin = 3;
+        for (int l = 0; l < net.n_conv; ++l) {
+            const int cout = net.chan[l], k = net.ksize, cs = net.conv_stride;
+            const int Ho = same_out(H, cs), pb = same_pad_before(H, k, cs);
+            // conv + bias + ReLU: bufA [H][H][cin] -> bufB [Ho][Ho][cout]
+            for (int i = tid; i < Ho * Ho * cout; i += FEAT_THREADS) {
+                const int co = i % cout, xo = (i / cout) % Ho, yo = i / (cout * Ho);
+                float acc = __ldg(net.b[l] + co);
+                for (int ky = 0; ky < k; ++ky) {
+                    const int yi = yo * cs + ky - pb;
+                    if (yi < 0 || yi >= H) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        const int xi = xo * cs + kx - pb;
+                        if (xi < 0 || xi >= H) continue;
+                        const float* in = bufA + ((int64_t)yi * H + xi) * cin;
+                        const float* wt = net.w[l] + ((int64_t)(ky * k + kx) * cin) * cout + co;
+                        for (int ci = 0; ci < cin; ++ci) acc = fmaf(in[ci], __ldg(wt + (int64_t)ci * cout), acc);
+                    }
+                }
+                bufB[i] = fmaxf(acc, 0.f);
+            }
+            __syncthreads();
+            // max pool SAME (padding excluded): bufB [Ho][Ho][cout] -> bufA [Hp][Hp][cout]
+            const int ps = net.pool_size, pst = net.pool_stride;
+            const int Hp = same_out(Ho, pst), ppb = same_pad_before(Ho, ps, pst);
+            for (int i = tid; i < Hp * Hp * cout; i += FEAT_THREADS) {
+                const int co = i % cout, xo = (i / cout) % Hp, yo = i / (cout * Hp);
+                float m = -INFINITY;
+                for (int ky = 0; ky < ps; ++ky) {
+                    const int yi = yo * pst + ky - ppb;
+                    if (yi < 0 || yi >= Ho) continue;
+                    for (int kx = 0; kx < ps; ++kx) {
+                        const int xi = xo * pst + kx - ppb;
+                        if (xi < 0 || xi >= Ho) continue;
+                        m = fmaxf(m, bufB[((int64_t)yi * Ho + xi) * cout + co]);
+                    }
+                }
+                bufA[i] = m;
+            }
+            __syncthreads();
+            H = Hp; cin = cout;
+        }
+        // ---- NHWC flatten -> output row
+        for (int64_t i = tid; i < K; i += FEAT_THREADS) {
+            const float v = bufA[i];
+            if (OUT_SPLIT) {
+                const float sv = v * a_scale;
+                const __half h = __float2half_rn(sv);
+                out_hi[wrel * K + i] = h;
+                out_lo[wrel * K + i] = __float2half_rn(sv - __half2float(h));
+            } else {
+                out_f32[wrel * K + i] = v;
+            }
+        }
+    }
+}
+
 int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     RODC_CHECK_ARG(src != nullptr, "window source is NULL");
     SrcDev d; memset(&d, 0, sizeof(d));
@@ -556,8 +672,24 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
 }
 
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
-                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st) {
+                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch) {
     if (n <= 0) return RODC_OK;
+    if (s->general) {
+        RODC_CHECK_ARG(general_scratch != nullptr, "general-architecture stage needs activation scratch");
+        RODC_CHECK_ARG(n < (1ll << 31), "too many windows in one launch");
+        GenNet net;
+        net.n_conv = s->n_conv; net.ksize = s->ksize; net.conv_stride = s->conv_stride;
+        net.pool_size = s->pool_size; net.pool_stride = s->pool_stride;
+        for (int l = 0; l < 8; ++l) { net.chan[l] = s->chan[l]; net.w[l] = s->gconv_w[l]; net.b[l] = s->gconv_b[l]; }
+        const unsigned grid = (unsigned)(n < GENERAL_CTAS ? n : GENERAL_CTAS);
+        const size_t smem = (size_t)6 * s->in_size * sizeof(int);
+        if (out_f32) features_general_kernel<0><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
+                                                                                  1.f, out_f32, nullptr, nullptr, s->K);
+        else features_general_kernel<1><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
+                                                                          ldexpf(1.f, s->a_exp), nullptr, out_hi, out_lo, s->K);
+        RODC_LAUNCH_CHECK();
+        return RODC_OK;
+    }
     RODC_CHECK_ARG(s->channels == 32, "feature kernel is built for 32 conv channels (got %d)", s->channels);
     RODC_CHECK_ARG((s->in_size & 3) == 0, "stage input size must be a multiple of 4 (got %d)", s->in_size);
     RODC_CHECK_ARG(n < (1ll << 31), "too many windows in one launch");

@@ -13,6 +13,7 @@ rodc_stage::~rodc_stage() {
     if (fc1_hi) cudaFree(fc1_hi);
     if (fc1_lo) cudaFree(fc1_lo);
     if (conv_frag) cudaFree(conv_frag);
+    for (int l = 0; l < 8; ++l) { if (gconv_w[l]) cudaFree(gconv_w[l]); if (gconv_b[l]) cudaFree(gconv_b[l]); }
     if (conv_frag_perm) cudaFree(conv_frag_perm);
 }
 
@@ -213,10 +214,79 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
     return RODC_OK;
 }
 
+extern "C" int rodc_stage_create_general(int in_size, int n_conv, const int32_t* channels, int ksize, int conv_stride,
+                                         int pool_size, int pool_stride,
+                                         const float* const* conv_w, const float* const* conv_b,
+                                         int fc1_size, int n_prev, const float* fc1_w, const float* fc1_b,
+                                         const float* fc2_w, const float* fc2_b, rodc_stage** out) {
+    RODC_CHECK_ARG(out && channels && conv_w && conv_b && fc1_w && fc1_b && fc2_w && fc2_b, "rodc_stage_create_general: NULL argument");
+    RODC_CHECK_ARG(n_conv >= 1 && n_conv <= 8, "rodc_stage_create_general: 1..8 conv layers (got %d)", n_conv);
+    RODC_CHECK_ARG(ksize >= 1 && ksize <= 11 && conv_stride >= 1 && pool_size >= 1 && pool_stride >= 1,
+                   "rodc_stage_create_general: bad geometry");
+    // the reference default takes the specialised kernels
+    if (n_conv == 1 && channels[0] == 32 && ksize == 3 && conv_stride == 1 && pool_size == 3 && pool_stride == 1 &&
+        in_size % 4 == 0 && fc1_size % 256 == 0)
+        return rodc_stage_create(in_size, 32, fc1_size, n_prev, conv_w[0], conv_b[0], fc1_w, fc1_b, fc2_w, fc2_b, out);
+    RODC_CHECK_ARG(in_size >= 1 && in_size <= 512, "rodc_stage_create_general: bad input size %d", in_size);
+    RODC_CHECK_ARG(fc1_size > 0 && fc1_size % 128 == 0, "rodc_stage_create_general: fc1_size must be a multiple of 128");
+    rodc_stage* s = new (std::nothrow) rodc_stage();
+    if (!s) { set_error("out of host memory"); return RODC_ERR_NOMEM; }
+    s->general = 1; s->in_size = in_size; s->fc1_size = fc1_size; s->n_prev = n_prev;
+    s->n_conv = n_conv; s->ksize = ksize; s->conv_stride = conv_stride; s->pool_size = pool_size; s->pool_stride = pool_stride;
+    if (cudaGetDevice(&s->device) != cudaSuccess) { set_error("no CUDA device"); delete s; return RODC_ERR_CUDA; }
+    int H = in_size, cin = 3, rc = RODC_OK;
+    int64_t max_act = (int64_t)in_size * in_size * 3;
+    double bound = 255.0;                                    // bound of the activations, for the fp16-split exponent
+    for (int l = 0; l < n_conv; ++l) {
+        const int cout = channels[l];
+        RODC_CHECK_ARG(cout >= 1 && cout <= 1024, "rodc_stage_create_general: bad channel count %d", cout);
+        s->chan[l] = cout;
+        const size_t nw = (size_t)ksize * ksize * cin * cout;
+        if ((rc = upload(&s->gconv_w[l], conv_w[l], nw)) || (rc = upload(&s->gconv_b[l], conv_b[l], cout))) { delete s; return rc; }
+        double worst = 0.0;
+        for (int co = 0; co < cout; ++co) {
+            double l1 = 0.0;
+            for (size_t t = 0; t < (size_t)ksize * ksize * cin; ++t) l1 += fabs((double)conv_w[l][t * cout + co]);
+            const double b = bound * l1 + fabs((double)conv_b[l][co]);
+            if (b > worst) worst = b;
+        }
+        bound = worst;
+        const int Ho = (H + conv_stride - 1) / conv_stride;
+        if ((int64_t)Ho * Ho * cout > max_act) max_act = (int64_t)Ho * Ho * cout;
+        H = (Ho + pool_stride - 1) / pool_stride;
+        cin = cout;
+    }
+    s->channels = cin;
+    s->K = (int64_t)H * H * cin;
+    s->max_act = max_act;
+    RODC_CHECK_ARG(s->K % 8 == 0, "rodc_stage_create_general: flattened size %lld must be a multiple of 8", (long long)s->K);
+    const size_t nfc1 = (size_t)s->K * fc1_size, nfc2 = (size_t)(fc1_size + n_prev) * 2;
+    if ((rc = upload(&s->fc1_w, fc1_w, nfc1)) || (rc = upload(&s->fc1_b, fc1_b, fc1_size)) ||
+        (rc = upload(&s->fc2_w, fc2_w, nfc2)) || (rc = upload(&s->fc2_b, fc2_b, 2))) { delete s; return rc; }
+    double wmax = 0.0;
+    for (size_t i = 0; i < nfc1; ++i) { double a = fabs((double)fc1_w[i]); if (a > wmax) wmax = a; }
+    s->a_exp = pow2_headroom(bound, 32768.0);
+    s->w_exp = pow2_headroom(wmax, 16384.0);
+    if (cudaMalloc(&s->fc1_hi, nfc1 * sizeof(__half)) != cudaSuccess || cudaMalloc(&s->fc1_lo, nfc1 * sizeof(__half)) != cudaSuccess) {
+        set_error("cudaMalloc of the split fc1 weights failed"); delete s; return RODC_ERR_NOMEM;
+    }
+    if ((rc = prepare_fc1_split(s, 0))) { delete s; return rc; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("weight preparation failed"); delete s; return RODC_ERR_CUDA; }
+    *out = s;
+    return RODC_OK;
+}
+
 extern "C" void rodc_stage_destroy(rodc_stage* s) { delete s; }
+
+// general-architecture stages keep two activation maps per persistent CTA at the END of the workspace
+static int64_t general_scratch_bytes(const rodc_stage* s) {
+    return s->general ? (int64_t)GENERAL_CTAS * 2 * s->max_act * 4 + 256 : 0;
+}
 
 // workspace = feature chunk: fp32 [m,K] (SIMT) or two fp16 planes [m,K] (tensor): 4*K bytes per window
 static int64_t chunk_windows(const rodc_stage* s, int64_t workspace_bytes) {
+    workspace_bytes -= general_scratch_bytes(s);
+    if (workspace_bytes < 0) return 0;
     int64_t m = workspace_bytes / (s->K * 4);
     if (m >= 128) m = m / 128 * 128;
     return m;
@@ -230,7 +300,7 @@ extern "C" int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, in
     const int64_t cap = 148 * 128 * (s->K > 40000 ? 1 : (s->K > 10000 ? 2 : 8));
     if (m > cap) m = cap;
     if (m < 128) m = 128;
-    return m * s->K * 4;
+    return m * s->K * 4 + general_scratch_bytes(s);
 }
 
 extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
@@ -246,19 +316,26 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
     RODC_CHECK_ARG(chunk >= 1, "rodc_stage_forward: workspace too small (%lld bytes, need >= %lld)",
                    (long long)workspace_bytes, (long long)(s->K * 4));
     cudaStream_t st = as_stream(stream);
+    float* gscratch = nullptr;
+    if (s->general) {
+        const int64_t off = (workspace_bytes - general_scratch_bytes(s) + 255) / 256 * 256;
+        gscratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off);
+        // the tensor fc1 needs fc1_size == 512 and K % 64 == 0; anything else runs the fp32 SIMT GEMM
+        if (impl == RODC_IMPL_TENSOR && (s->fc1_size != 512 || s->K % 64 != 0)) impl = RODC_IMPL_SIMT;
+    }
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t m = (n - c0) < chunk ? (n - c0) : chunk;
         float* bott = bottleneck + c0 * ld_bott;
         if (impl == RODC_IMPL_SIMT) {
             float* feat = reinterpret_cast<float*>(workspace);
-            if ((rc = launch_features(s, sd, first + c0, m, feat, nullptr, nullptr, st))) return rc;
+            if ((rc = launch_features(s, sd, first + c0, m, feat, nullptr, nullptr, st, gscratch))) return rc;
             profile_begin(st);
             if ((rc = launch_fc1_simt(s, feat, m, bott, ld_bott, st))) return rc;
             profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         } else {
             __half* hi = reinterpret_cast<__half*>(workspace);
             __half* lo = hi + m * s->K;
-            if ((rc = launch_features(s, sd, first + c0, m, nullptr, hi, lo, st))) return rc;
+            if ((rc = launch_features(s, sd, first + c0, m, nullptr, hi, lo, st, gscratch))) return rc;
             profile_begin(st);
             if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
             profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
@@ -270,6 +347,7 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
 extern "C" int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, int64_t first,
                                        int64_t n, float* features, void* stream) {
     RODC_CHECK_ARG(s && src && features, "rodc_stage_features_f32: NULL argument");
+    if (s->general) { set_error("rodc_stage_features_f32 is a test hook of the default architecture only"); return RODC_ERR_UNSUP; }
     SrcDev sd;
     int rc = resolve_source(src, s->in_size, &sd); if (rc) return rc;
     return launch_features(s, sd, first, n, features, nullptr, nullptr, as_stream(stream));

@@ -24,6 +24,13 @@ struct rodc_stage {
     int c_exp = 0;              // conv weights are scaled by 2^c_exp before the fp16 split
     int a_exp = 0;              // features are scaled by 2^a_exp before the fp16 split
     int w_exp = 0;              // weights  are scaled by 2^w_exp before the fp16 split
+    // general architecture (several conv layers / other strides, network/net.py:189-221): layer table
+    int general = 0;
+    int n_conv = 1, ksize = 3, conv_stride = 1, pool_size = 3, pool_stride = 1;
+    int chan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float* gconv_w[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* gconv_b[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t max_act = 0;        // floats of the largest activation map (per ping-pong buffer)
     ~rodc_stage();
 };
 
@@ -42,7 +49,8 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out);
 
 // features.cu
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
-                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st);
+                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch = nullptr);
+constexpr int GENERAL_CTAS = 296;     // persistent CTAs of the general-architecture feature kernel
 // fc.cu
 int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bott, int ld_bott, cudaStream_t st);
 int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st);

@@ -36,12 +36,13 @@ class CascadeEngine:
     single-net decision rule (argmax != background, confidence = p[argmax])."""
 
     def __init__(self, stage_weights: Sequence[Dict[str, np.ndarray]], device: Optional[int] = None,
-                 single: bool = False):
+                 single: bool = False, geometries: Optional[Sequence[Optional[Dict[str, int]]]] = None):
         if not torch.cuda.is_available():
             raise native._lib.RodcError("CascadeEngine needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         with torch.cuda.device(self.device):
-            self.stages = [native.Stage(w, self.device) for w in stage_weights]
+            geos = list(geometries) if geometries is not None else [None] * len(stage_weights)
+            self.stages = [native.Stage(w, self.device, g) for w, g in zip(stage_weights, geos)]
         self.single = single
         self.sizes = [s.in_size for s in self.stages]
         self._plans: Dict[Tuple, native.Plan] = {}

@@ -169,31 +169,45 @@ def recrop(table: FrameTable, meta: torch.Tensor, size: int) -> torch.Tensor:
 
 # --------------------------------------------------------------------------------- stage
 class Stage:
-    """One stage net on the device (weights in the reference's layouts, see stage_model.py)."""
+    """One stage net on the device (weights in the reference's layouts, see network/stage_model.py).
+    ``geometry`` = dict(in_size, conv_stride, pool_size, pool_stride) for non-default architectures."""
 
-    def __init__(self, weights: Dict[str, np.ndarray], device=None):
+    def __init__(self, weights: Dict[str, np.ndarray], device=None, geometry: Optional[Dict[str, int]] = None):
         if not torch.cuda.is_available():
             raise _lib.RodcError("a CUDA device is required (no CPU fallback)")
-        cw = np.ascontiguousarray(weights["conv0_W"], np.float32)
-        assert cw.shape[:3] == (3, 3, 3), "default architecture: one 3x3 conv over RGB"
-        self.channels = int(cw.shape[3])
+        geo = dict(conv_stride=1, pool_size=3, pool_stride=1)
+        geo.update(geometry or {})
+        n_conv = 0
+        while "conv%d_W" % n_conv in weights:
+            n_conv += 1
+        cws = [np.ascontiguousarray(weights["conv%d_W" % j], np.float32) for j in range(n_conv)]
+        cbs = [np.ascontiguousarray(weights["conv%d_b" % j], np.float32) for j in range(n_conv)]
+        ksize = int(cws[0].shape[0])
+        chans = np.asarray([c.shape[3] for c in cws], np.int32)
+        self.channels = int(chans[-1])
         f1 = np.ascontiguousarray(weights["fc1_W"], np.float32)
         self.K, self.fc1_size = int(f1.shape[0]), int(f1.shape[1])
-        self.in_size = int(round((self.K // self.channels) ** 0.5))
-        assert self.in_size * self.in_size * self.channels == self.K
+        if "in_size" in geo:
+            self.in_size = int(geo["in_size"])
+        else:
+            self.in_size = int(round((self.K // self.channels) ** 0.5))
+            assert self.in_size * self.in_size * self.channels == self.K, "pass geometry['in_size'] for strided nets"
         f2 = np.ascontiguousarray(weights["fc2_W"], np.float32)
         self.n_prev = int(f2.shape[0]) - self.fc1_size
         self.width = self.fc1_size + self.n_prev
-        arrs = [cw, np.ascontiguousarray(weights["conv0_b"], np.float32), f1,
-                np.ascontiguousarray(weights["fc1_b"], np.float32), f2,
-                np.ascontiguousarray(weights["fc2_b"], np.float32)]
+        f1b = np.ascontiguousarray(weights["fc1_b"], np.float32)
+        f2b = np.ascontiguousarray(weights["fc2_b"], np.float32)
         h = C.c_void_p()
+        wptr = (C.c_void_p * n_conv)(*[c.ctypes.data for c in cws])
+        bptr = (C.c_void_p * n_conv)(*[c.ctypes.data for c in cbs])
         ctx = torch.cuda.device(device) if device is not None else torch.cuda.device(torch.cuda.current_device())
         with ctx:
             torch.cuda.init()
-            check(_lib.lib().rodc_stage_create(self.in_size, self.channels, self.fc1_size, self.n_prev,
-                                               *[C.c_void_p(a.ctypes.data) for a in arrs], C.byref(h)),
-                  "rodc_stage_create")
+            check(_lib.lib().rodc_stage_create_general(
+                self.in_size, n_conv, chans.ctypes.data_as(_lib.c_i32p), ksize, int(geo["conv_stride"]),
+                int(geo["pool_size"]), int(geo["pool_stride"]), wptr, bptr, self.fc1_size, self.n_prev,
+                C.c_void_p(f1.ctypes.data), C.c_void_p(f1b.ctypes.data), C.c_void_p(f2.ctypes.data),
+                C.c_void_p(f2b.ctypes.data), C.byref(h)), "rodc_stage_create_general")
         self._h = h
 
     @property

@@ -20,28 +20,60 @@ import numpy as np
 
 from .. import synth
 
-KEYS = ("conv0_W", "conv0_b", "fc1_W", "fc1_b", "fc2_W", "fc2_b")
 
 
 class StageModel:
-    def __init__(self, weights: Dict[str, np.ndarray]):
-        for k in KEYS:
+    """Weights + geometry of one stage.  ``in_size`` must be given for nets whose spatial size changes
+    (strides > 1); for the default stride-1 nets it follows from the fc1 shape."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], in_size: Optional[int] = None, conv_stride: int = 1,
+                 pool_size: int = 3, pool_stride: int = 1):
+        n_conv = 0
+        while "conv%d_W" % n_conv in weights:
+            n_conv += 1
+        if n_conv < 1:
+            raise ValueError("stage model lacks conv0_W")
+        for k in ("fc1_W", "fc1_b", "fc2_W", "fc2_b"):
             if k not in weights:
                 raise ValueError("stage model lacks %s" % k)
-        if "conv1_W" in weights:
-            raise NotImplementedError("multi-conv-layer stage nets are not built yet (SURVEY.md §8f #4)")
-        self.weights = {k: np.ascontiguousarray(weights[k], np.float32) for k in KEYS}
+        keys = ["conv%d_%s" % (j, t) for j in range(n_conv) for t in ("W", "b")] + ["fc1_W", "fc1_b", "fc2_W", "fc2_b"]
+        for k in keys:
+            if k not in weights:
+                raise ValueError("stage model lacks %s" % k)
+        self.weights = {k: np.ascontiguousarray(weights[k], np.float32) for k in keys}
+        self.n_conv = n_conv
+        self.conv_stride, self.pool_size, self.pool_stride = int(conv_stride), int(pool_size), int(pool_stride)
         cw = self.weights["conv0_W"]
-        if cw.shape[:3] != (3, 3, 3):
-            raise NotImplementedError("only the default 3x3 RGB conv is built (got %r)" % (cw.shape,))
-        self.channels = int(cw.shape[3])
+        if cw.ndim != 4 or cw.shape[0] != cw.shape[1] or cw.shape[2] != 3:
+            raise ValueError("conv0_W must be HWIO [k,k,3,C] (got %r)" % (cw.shape,))
+        self.ksize = int(cw.shape[0])
+        self.conv_channels = [int(self.weights["conv%d_W" % j].shape[3]) for j in range(n_conv)]
+        self.channels = self.conv_channels[-1]
         k, self.fc1_size = self.weights["fc1_W"].shape
-        self.in_size = int(round((k // self.channels) ** 0.5))
-        if self.in_size * self.in_size * self.channels != k:
-            raise ValueError("fc1 rows %d are not S*S*%d" % (k, self.channels))
+
+        def flat_size(side):
+            for _ in range(n_conv):
+                side = -(-side // self.conv_stride)
+                side = -(-side // self.pool_stride)
+            return side * side * self.channels
+        if in_size is None:
+            cands = [s_ for s_ in range(1, 1025) if flat_size(s_) == k]
+            if not cands:
+                raise ValueError("fc1 rows %d do not match any input size" % k)
+            in_size = cands[0] if len(cands) == 1 or self.conv_stride * self.pool_stride == 1 else None
+            if in_size is None:
+                raise ValueError("ambiguous input size for a strided net: pass in_size")
+        self.in_size = int(in_size)
+        if flat_size(self.in_size) != k:
+            raise ValueError("fc1 rows %d are not the flattened size of a %dx%d input" % (k, self.in_size, self.in_size))
         self.n_prev = int(self.weights["fc2_W"].shape[0]) - int(self.fc1_size)
         if self.n_prev < 0 or self.weights["fc2_W"].shape[1] != 2:
             raise ValueError("bad fc2 shape %r" % (self.weights["fc2_W"].shape,))
+
+    @property
+    def is_default_architecture(self) -> bool:
+        return (self.n_conv == 1 and self.conv_channels == [32] and self.ksize == 3 and self.conv_stride == 1
+                and self.pool_size == 3 and self.pool_stride == 1)
 
     # X placeholder shape of the exported graph: [None, H, W, 3] (`app/train_app.py:203-205`)
     @property
@@ -59,7 +91,8 @@ class StageModel:
     def save(self, path: str):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         with open(path, "wb") as f:
-            np.savez(f, **self.weights)
+            np.savez(f, in_size=self.in_size, conv_stride=self.conv_stride, pool_size=self.pool_size,
+                     pool_stride=self.pool_stride, **self.weights)
 
     @staticmethod
     def load(path: str) -> "StageModel":
@@ -67,7 +100,9 @@ class StageModel:
             from .graph_pb import read_stage_pb
             return StageModel(read_stage_pb(path))
         with np.load(path) as z:
-            return StageModel({k: z[k] for k in z.files})
+            d = {k: z[k] for k in z.files}
+        geo = {k: int(d.pop(k)) for k in ("in_size", "conv_stride", "pool_size", "pool_stride") if k in d}
+        return StageModel(d, **geo)
 
 
 def xavier_cascade_models(n_stages: int = 3, img_max: int = 48,

@@ -67,24 +67,27 @@ def xavier_stage_weights(stage: int, in_size: int, *, n_prev_bottleneck: int = 0
                          conv_filters: Sequence[int] = (32,), ksize: int = 3,
                          fc1_size: int = 512, n_classes: int = 2,
                          fg_bias_offset: float = 0.0,
-                         seed: Optional[int] = None) -> Dict[str, np.ndarray]:
+                         seed: Optional[int] = None, conv_stride: int = 1, pool_stride: int = 1) -> Dict[str, np.ndarray]:
     """Random-init weights of one stage net in the reference's layouts.
 
     conv ``W[kh,kw,Cin,Cout]`` (HWIO), fc1 ``W[K,512]`` with NHWC flatten order,
     fc2 ``W[512 + n_prev_bottleneck, 2]``; biases zero.  ``fg_bias_offset`` is the
     documented calibration knob added to ``fc2.b[1]`` for configs that need a
     target pass rate (the same offset feeds the oracle and the GPU path).
-    Assumes stride-1 SAME conv/pool (reference defaults), so the spatial size
-    stays ``in_size`` up to the flatten.
+    SAME conv/pool: every layer maps a side ``n`` to ``ceil(n / stride)`` (stride 1 = reference default keeps
+    ``in_size`` up to the flatten).
     """
     rs = np.random.RandomState(1000 + stage if seed is None else seed)
     w: Dict[str, np.ndarray] = {}
     cin = 3
+    side = in_size
     for j, cout in enumerate(conv_filters):
         w["conv%d_W" % j] = _xavier(rs, (ksize, ksize, cin, cout), ksize * ksize * cin, ksize * ksize * cout)
         w["conv%d_b" % j] = np.zeros((cout,), np.float32)
         cin = cout
-    k = in_size * in_size * cin
+        side = -(-side // conv_stride)
+        side = -(-side // pool_stride)
+    k = side * side * cin
     w["fc1_W"] = _xavier(rs, (k, fc1_size), k, fc1_size)
     w["fc1_b"] = np.zeros((fc1_size,), np.float32)
     k2 = fc1_size + n_prev_bottleneck

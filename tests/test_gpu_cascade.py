@@ -258,3 +258,29 @@ def test_no_bottleneck_reuse_and_launch_chunking(pkg):
     r = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64)
     ref = np.column_stack([r.image, r.boxes, r.conf]).astype(np.float64).reshape(-1, 6)
     assert np.array_equal(g, ref)
+
+
+def test_cascade_with_two_conv_layers(pkg):
+    """conv_filter_sizes = [16, 32] (two conv+ReLU+pool blocks per stage) end to end against the fp64 oracle."""
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    pkg.cf.set("min_window_length", 0.2)
+    ocfg = oc.Config(min_window_length=0.2)
+
+    def nets(offsets):
+        return [synth.xavier_stage_weights(i, s, n_prev_bottleneck=512 * i, conv_filters=(16, 32), fg_bias_offset=o)
+                for i, (s, o) in enumerate(zip((12, 24, 48), offsets))]
+    frames = [synth.synth_frame(110, 150, 41)]
+    offsets = oc.calibrate_offsets(frames, nets([0, 0, 0]), ocfg, [0.5, 0.5, 0.5])
+    weights = nets(offsets)
+    models = [pkg.StageModel(w) for w in weights]
+    assert [m.n_conv for m in models] == [2, 2, 2] and not models[0].is_default_architecture
+    app = pkg.InferenceCascadeApp("ml", stage_models=models)
+    got = app.run_inference_on_images([pkg.ArrayImageInfo(frames[0], "ml.png")], merge=True)
+    g = np.asarray([[b.xmin, b.ymin, b.xmax, b.ymax, b.confidence] for b in got[0]], np.float64).reshape(-1, 5)
+    r = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64)
+    ref = np.column_stack([r.boxes, r.conf]).astype(np.float64).reshape(-1, 5)
+    res = app._engine.run_frames(np.stack(frames), keep_trace=True)
+    for i, st in enumerate(r.stages):
+        assert np.array_equal(res.trace["keep"][i].cpu().numpy(), st.keep_idx)
+    assert np.array_equal(g, ref)

@@ -338,3 +338,39 @@ np.save(sys.argv[1], logits.cpu().numpy())
         subprocess.run([sys.executable, "-c", code % REPO, path], check=True, env=env, timeout=300)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])          # same MMA order -> bit-identical
+
+
+@pytest.mark.parametrize("spec", [
+    dict(S=24, filters=(16, 32), ksize=3, conv_stride=1, pool_size=2, pool_stride=2, n_prev=512),
+    dict(S=48, filters=(24,), ksize=5, conv_stride=2, pool_size=3, pool_stride=2, n_prev=0),
+    dict(S=12, filters=(8, 16, 32), ksize=3, conv_stride=1, pool_size=3, pool_stride=1, n_prev=0),
+])
+def test_general_stage_architectures_match_fp64_oracle(nat, spec):
+    """Several conv layers / strides (`network/net.py:189-221`, TF SAME padding) through the generic kernel."""
+    from oracle import stage_net
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    S = spec["S"]
+    w = synth.xavier_stage_weights(1, S, n_prev_bottleneck=spec["n_prev"], conv_filters=spec["filters"], ksize=spec["ksize"],
+                                   conv_stride=spec["conv_stride"], pool_stride=spec["pool_stride"])
+    rs = np.random.RandomState(1)
+    for j in range(len(spec["filters"])):
+        w["conv%d_b" % j] = (rs.randn(spec["filters"][j]) * 0.5).astype(np.float32)
+    n = 150
+    frame = synth.synth_frame(S * 5, S * 6, 77)
+    ys = rs.randint(0, frame.shape[0] - S, n); xs = rs.randint(0, frame.shape[1] - S, n)
+    x = np.stack([frame[y:y + S, x_:x_ + S] for y, x_ in zip(ys, xs)])
+    prev = (rs.rand(n, spec["n_prev"]).astype(np.float32) * 20.0) if spec["n_prev"] else None
+    geo = dict(in_size=S, conv_stride=spec["conv_stride"], pool_size=spec["pool_size"], pool_stride=spec["pool_stride"])
+    st = nat.Stage(w, geometry=geo)
+    assert st.K == w["fc1_W"].shape[0]
+    for impl in (nat.IMPL_TENSOR, nat.IMPL_SIMT):
+        bott = torch.zeros((n, st.width), dtype=torch.float32, device="cuda")
+        if prev is not None:
+            bott[:, 512:] = dev(prev)
+        ws = torch.empty((st.workspace_bytes(n, impl),), dtype=torch.uint8, device="cuda")
+        logits, probs = nat.stage_forward(st, nat.make_source(dense=dev(x)), 0, n, bott, ws, impl)
+        p64, b64, l64, _ = stage_net.stage_forward(x, w, prev, dtype=torch.float64, conv_stride=spec["conv_stride"],
+                                                   pool_size=spec["pool_size"], pool_stride=spec["pool_stride"])
+        l64 = l64.numpy()
+        assert np.abs(logits.cpu().numpy() - l64).max() <= 2e-5 * max(np.abs(l64).max(), 1.0)
+        np.testing.assert_allclose(bott.cpu().numpy()[:, :512], b64.numpy()[:, :512], rtol=1e-4, atol=2e-5 * np.abs(b64.numpy()).max())
