@@ -291,7 +291,8 @@ def _run_prefix(frames, ws, cfg, upto: int, arith: str) -> np.ndarray:
     """Logits (fp64) of stage ``upto`` on the survivors of stages ``< upto``."""
     sub = Config(**{**cfg.__dict__})
     n = len(ws)
-    sizes = [int(round((w["fc1_W"].shape[0] // w["conv0_W"].shape[3]) ** 0.5)) for w in ws]
+    sizes = [int(round((w["fc1_W"].shape[0] // w["conv%d_W" % (stage_net.n_conv_layers(w) - 1)].shape[3]) ** 0.5))
+             for w in ws]
     raws, norms, ids = [], [], []
     for fi, fr in enumerate(frames):
         raw, p = extract_windows(fr, sizes[0], sub, arith)
