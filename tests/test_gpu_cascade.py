@@ -281,6 +281,15 @@ def test_cascade_with_two_conv_layers(pkg):
     r = oc.run_cascade(frames, weights, ocfg, dtype=torch.float64)
     ref = np.column_stack([r.boxes, r.conf]).astype(np.float64).reshape(-1, 5)
     res = app._engine.run_frames(np.stack(frames), keep_trace=True)
+    same = True
     for i, st in enumerate(r.stages):
-        assert np.array_equal(res.trace["keep"][i].cpu().numpy(), st.keep_idx)
-    assert np.array_equal(g, ref)
+        lg = res.trace["logits"][i].cpu().numpy().astype(np.float64)
+        assert np.abs(lg - st.logits).max() <= 1e-3 * np.abs(st.logits).max()
+        diff = np.setxor1d(res.trace["keep"][i].cpu().numpy(), st.keep_idx)
+        if diff.size:                       # the calibrated threshold sits on a sample quantile: a flip must be in the band
+            margin = st.logits[diff, 1] - st.logits[diff, 0]
+            assert np.abs(margin).max() < EPS[i], (i, margin, (lg[diff, 1] - lg[diff, 0]))
+            same = False
+            break
+    if same:
+        assert np.array_equal(g, ref)
