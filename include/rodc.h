@@ -86,6 +86,38 @@ int rodc_window_meta(rodc_plan* p, int n_frames, int frame_id_base, int32_t* met
 int rodc_window_gather_rows(rodc_plan* p, int n_frames, int64_t pyramid_base_off, int64_t* win_off,
                             int32_t* win_pitch, void* stream);
 
+/* Level index (+ slot_base) of every stage-0 window, same order as rodc_window_meta:
+ *   out [n_frames * n_windows] i32.  It is the window's key into a rodc_scaled_slot table. */
+int rodc_window_levels(rodc_plan* p, int n_frames, int slot_base, int32_t* out, void* stream);
+/* out[i] = in[idx[i]] for rows of row_bytes (multiple of 4): carries per-window bookkeeping (level slots,
+ * GATHER rows) through the survivor lists that rodc_compact returns, like the reference's
+ * windows_info_new.append(windows_info[window_index_original]) (inference_cascade_app.py:219-240). */
+int rodc_select_rows(const void* in, const int32_t* idx, int64_t n, int row_bytes, void* out, void* stream);
+
+/* ---------------------------------------------------------------- resize-then-crop branch
+ * cf cascade_scale_patches_individually=False (inference_cascade_app.py:374-394): the next stage's input
+ * of a survivor is a size x size crop at (int(xmin_norm * next_scale), int(ymin_norm * next_scale)) of the
+ * WHOLE frame resized to next_scale = window.scale * size / window.width (image.raw_scaled ->
+ * scipy.misc.imresize, data/image_info.py:201-250).  rodc_plan_create_scales + rodc_pyramid build those
+ * frames (same integer-exact Pillow resampler as the stage-0 pyramid); rodc_window_scaled_rows turns the
+ * survivors into GATHER rows over them. */
+int rodc_plan_create_scales(int img_w, int img_h, int n_scales, const double* scales, rodc_plan** out);
+typedef struct rodc_scaled_slot {
+    double  scale;          /* next_scale of this (frame group, level)                                   */
+    int64_t base_off;       /* byte offset of the level of the group's FIRST frame from gather_base      */
+    int64_t frame_stride;   /* bytes between consecutive frames of the group (0: a single frame)         */
+    int32_t width, height;  /* size of the resized frame                                                 */
+    int32_t frame_base;     /* frame id (meta column 0) of the group's first frame                       */
+    int32_t individually;   /* 1: this window keeps the crop + cv2.resize input (iff_not_cached option): */
+                            /*    row i points at dense_rel_off + i * size*size*3, pitch size*3          */
+} rodc_scaled_slot;
+/*   meta [n,5] i32, slot [n] i32 (index into slots), slots: DEVICE array of n_slots entries,
+ *   win_off [n] i64 / win_pitch [n] i32 out, err: DEVICE i32, bit 0 set when a crop leaves its resized
+ *   frame (Window.raw raises ValueError, data/rectangles.py:286-289), bit 1 on a bad slot index. */
+int rodc_window_scaled_rows(const int32_t* meta, const int32_t* slot, int64_t n, const rodc_scaled_slot* slots,
+                            int n_slots, int size, int64_t dense_rel_off, int64_t* win_off, int32_t* win_pitch,
+                            int32_t* err, void* stream);
+
 /* ---------------------------------------------------------------- K4 recrop
  * Replaces _get_increased_raw_window_for_next_net (inference_cascade_app.py:363-373):
  * cv2.resize(window.raw_norm, (size,size)), INTER_LINEAR 8U fixed point incl. the 2x
@@ -136,7 +168,13 @@ typedef struct {
 } rodc_window_source;
 
 #define RODC_IMPL_TENSOR 0   /* tcgen05 split-fp16 GEMM (3 MMAs, fp32-grade)                 */
-#define RODC_IMPL_SIMT   1   /* fp32 CUDA-core GEMM (cross-check implementation)             */
+#define RODC_IMPL_SIMT   1   /* The u8 input of a stage for any window source: out [n,size,size,3] u8 = the reference's windows_raw
+ * slice fed to X (inference_cascade_app.py:200-202).  API / parity path (the stage kernels read the sources
+ * in place); for RODC_SRC_PYRAMID it equals rodc_extract_windows, for RODC_SRC_RECROP rodc_recrop. */
+int rodc_source_windows(const rodc_window_source* src, int64_t first, int64_t n, int size, uint8_t* out,
+                        void* stream);
+
+/* fp32 CUDA-core GEMM (cross-check implementation)             */
 
 int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, int impl);
 /* Forward of windows [first, first+n) of `src`.

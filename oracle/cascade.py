@@ -4,8 +4,10 @@ Restates
 * window extraction `data/rectangles.py:309-435` (+ per-scale level cache
   `data/image_info.py:201-250`),
 * merge-mode orchestration `app/abstract_inference_app.py:38-156`,
-* the cascade loop `app/inference_cascade_app.py:119-342` and the re-crop
-  `:346-373` (default branch ``cascade_scale_patches_individually=True``),
+* the cascade loop `app/inference_cascade_app.py:119-342` and the next-stage input
+  `:346-401`: crop + ``cv2.resize`` (default, `:363-373`), resize-then-crop
+  (``cascade_scale_patches_individually=False`` / ``..._iff_not_cached``, `:374-394`),
+  and the unchanged raw windows of cascades with one input size (`:234-240`),
 * the single-net path `app/inference_app.py:117-166`,
 * ``_run_nms`` / ``_postprocess_bboxes`` `app/inference_app.py:169-231` and
   ``vertically_enlarge_bboxes`` `data/rectangles.py:185-220`.
@@ -38,6 +40,8 @@ class Config:
     final_confidence_calculation: str = "FINAL_CONFIDENCE_CALCULATION_LAST_STEP"   # :118-122
     max_batch_size_original: int = 1200                 # :133,582
     reuse_bottlenecks: bool = True                      # :277
+    cascade_scale_patches_individually: bool = True     # :351
+    cascade_scale_patches_individually_iff_not_cached: bool = False   # :358
 
 
 MIN_SCORE_MULT = 0.5001   # `config.py:121`
@@ -84,6 +88,58 @@ def recrop(frame: np.ndarray, norm_box: Sequence[int], size: int, arith: str = "
         import cv2
         return cv2.resize(crop, (size, size))
     return cv_resize.cv_resize_linear(np.ascontiguousarray(crop), size, size)
+
+
+class ScaledCache:
+    """``ImageInfo._raw_img_cache`` of one frame for the keys ``orig_scaled_<ratio>``
+    (`data/image_info.py:201-258`): ``raw_scaled(True, ratio)`` resizes the ORIGINAL with
+    ``scipy.misc.imresize(arr, ratio)`` -> Pillow BILINEAR to ``(int(W*ratio), int(H*ratio))``."""
+
+    def __init__(self, frame: np.ndarray, arith: str = "restated"):
+        self.frame, self.arith, self.store, self.keys = frame, arith, {}, set()
+
+    def is_cached(self, ratio: float) -> bool:              # `:256-258`
+        return "orig_scaled_{}".format(ratio) in self.keys
+
+    def raw_scaled(self, ratio: float) -> np.ndarray:       # `:201-213`, always called with cache=True on this path
+        if ratio == 1.0:
+            return self.frame
+        key = "orig_scaled_{}".format(ratio)
+        self.keys.add(key)
+        if key not in self.store:
+            h, w = self.frame.shape[:2]
+            lw, lh = int(w * ratio), int(h * ratio)
+            if self.arith == "lib":
+                from PIL import Image
+                self.store[key] = np.asarray(Image.fromarray(self.frame).resize((lw, lh), resample=2))
+            else:
+                self.store[key] = pillow_resize.resize_bilinear(self.frame, lw, lh)
+        return self.store[key]
+
+
+def recrop_scaled(cache: ScaledCache, norm_box: Sequence[int], scale: float, width: int, size: int) -> np.ndarray:
+    """`app/inference_cascade_app.py:358-359,374-394`: crop ``size x size`` at
+    ``(int(xmin_norm * next_scale), int(ymin_norm * next_scale))`` of the frame resized to
+    ``next_scale = window.scale * (size / window.width)``; ``Window.raw`` bounds check `data/rectangles.py:286-289`."""
+    next_scale = scale * (size / width)
+    nx = int(int(norm_box[0]) * next_scale)
+    ny = int(int(norm_box[1]) * next_scale)
+    img = cache.raw_scaled(next_scale)
+    if ny + size > img.shape[0]:
+        raise ValueError("ymax must not leave the image boundaries")
+    if nx + size > img.shape[1]:
+        raise ValueError("xmax must not leave the image boundaries")
+    return img[ny:ny + size, nx:nx + size]
+
+
+def next_stage_window(frame: np.ndarray, cache: ScaledCache, norm_box, scale: float, width: int, size: int,
+                      cfg: "Config", arith: str) -> np.ndarray:
+    """``_get_increased_raw_window_for_next_net`` `:346-401` with its branch condition `:362-365`."""
+    next_scale = scale * (size / width)
+    if cfg.cascade_scale_patches_individually and \
+            (not cfg.cascade_scale_patches_individually_iff_not_cached or not cache.is_cached(next_scale)):
+        return recrop(frame, norm_box, size, arith)
+    return recrop_scaled(cache, norm_box, scale, width, size)
 
 
 # ----------------------------------------------------------------------------- nms / post
@@ -173,7 +229,8 @@ def run_cascade(frames: Sequence[np.ndarray], stage_weights: Sequence[Dict[str, 
     n_stages = len(stage_weights)
     sizes = [int(round((w["fc1_W"].shape[0] // w["conv%d_W" % (stage_net.n_conv_layers(w) - 1)].shape[3]) ** 0.5))
              for w in stage_weights]
-    raws, norms, img_ids = [], [], []
+    raws, norms, img_ids, wscales = [], [], [], []
+    caches: Dict[int, ScaledCache] = {}
     for fi, frame in enumerate(frames):
         try:
             raw, p = extract_windows(frame, sizes[0], cfg, arith)
@@ -182,9 +239,16 @@ def run_cascade(frames: Sequence[np.ndarray], stage_weights: Sequence[Dict[str, 
         except ValueError:
             continue
         raws.append(raw); norms.append(p.norm); img_ids.append(np.full(p.n_windows, fi, np.int64))
+        lv_scale = np.asarray([lv.scale for lv in p.levels], np.float64)
+        wscales.append(lv_scale[p.win_level])
+        caches[fi] = ScaledCache(frame, arith)
+        for li, lv in enumerate(p.levels):         # Window.raw cached every level it touched (`data/rectangles.py:281`)
+            if lv.scale != 1.0 and (p.win_level == li).any():
+                caches[fi].keys.add("orig_scaled_{}".format(lv.scale))         # pixels are rebuilt on first use
     if not raws:
         raise ValueError("Could not extract any windows from the given image")
     windows_raw = np.concatenate(raws); norm = np.concatenate(norms); image = np.concatenate(img_ids)
+    wscale = np.concatenate(wscales)
     orig = np.arange(windows_raw.shape[0])
     res = CascadeResult(n_windows=windows_raw.shape[0])
     bott_in = None
@@ -212,7 +276,7 @@ def run_cascade(frames: Sequence[np.ndarray], stage_weights: Sequence[Dict[str, 
         res.stages.append(StageTrace(windows_raw.shape[0], probs.numpy().astype(np_dtype),
                                      logits.numpy().astype(np_dtype), keep,
                                      windows_raw if keep_raw else None))
-        norm, image, orig = norm[keep], image[keep], orig[keep]
+        norm, image, orig, wscale = norm[keep], image[keep], orig[keep], wscale[keep]
         last = i == n_stages - 1
         if not last:
             bott_in = bott[keep] if cfg.reuse_bottlenecks else None
@@ -220,7 +284,8 @@ def run_cascade(frames: Sequence[np.ndarray], stage_weights: Sequence[Dict[str, 
             if nxt != sizes[i]:
                 new_raw = np.empty((keep.shape[0], nxt, nxt, 3), np.uint8)
                 for k in range(keep.shape[0]):                          # :301-304
-                    new_raw[k] = recrop(frames[image[k]], norm[k], nxt, arith)
+                    new_raw[k] = next_stage_window(frames[image[k]], caches[int(image[k])], norm[k], float(wscale[k]),
+                                                   sizes[0], nxt, cfg, arith)
                 windows_raw = new_raw
             else:
                 windows_raw = windows_raw[keep]

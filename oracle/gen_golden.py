@@ -57,6 +57,18 @@ CASES = {
                               cf=dict(min_window_length=0.2,
                                       final_confidence_calculation="FINAL_CONFIDENCE_CALCULATION_MULT",
                                       nms="NMS_DISABLED"), rates=[0.5, 0.5, 0.5]),
+    # next-stage input by resize-then-crop (`app/inference_cascade_app.py:374-394`)
+    "cascade_scaled_patches": dict(frames=[(120, 160, 8), (96, 128, 9)],
+                                   cf=dict(min_window_length=0.2, cascade_scale_patches_individually=False),
+                                   rates=[0.4, 0.5, 0.5]),
+    # ..._iff_not_cached with window_scale_factor 2: 2 * scale_k IS a cached level, so both branches are taken
+    "cascade_iff_not_cached": dict(frames=[(200, 260, 10)],
+                                   cf=dict(min_window_length=0.1, window_scale_factor=2.0,
+                                           cascade_scale_patches_individually_iff_not_cached=True),
+                                   rates=[0.6, 0.6, 0.6]),
+    # all stages share one input size: the raw stage-0 windows are carried through (`:234-240`)
+    "cascade_equal_dims": dict(frames=[(120, 160, 11)], cf=dict(min_window_length=0.2), rates=[0.4, 0.5, 0.5],
+                               sizes=[24, 24, 24]),
     "single_small": dict(frames=[(200, 260, 7)], cf=dict(min_window_length=0.3), rates=[0.3], single=True),
 }
 
@@ -75,6 +87,8 @@ def run_case(name: str, spec: dict):
     ocfg = ocascade.Config(**{k: v for k, v in spec["cf"].items() if k in ocascade.Config().__dict__})
     if single:
         weights = [synth.xavier_stage_weights(2, 48)]
+    elif spec.get("sizes"):
+        weights = [synth.xavier_stage_weights(i, sz, n_prev_bottleneck=512 * i) for i, sz in enumerate(spec["sizes"])]
     else:
         weights = synth.xavier_cascade()
     offsets = [0.0] * len(weights)
@@ -158,7 +172,7 @@ def run_case(name: str, spec: dict):
         out["cand_boxes"] = out["final_boxes"].copy()
     app.clean()
 
-    meta = dict(name=name, frames=spec["frames"], cf=spec["cf"], offsets=offsets, single=single,
+    meta = dict(name=name, frames=spec["frames"], cf=spec["cf"], offsets=offsets, single=single, sizes=spec.get("sizes"),
                 n_windows=int(raw0.shape[0]),
                 survivors=[int(out["stage%d_n_in" % i]) for i in range(len(stage_names))],
                 n_final=int(out["final_boxes"].shape[0]), n_cand=int(out["cand_boxes"].shape[0]))

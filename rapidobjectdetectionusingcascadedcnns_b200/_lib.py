@@ -27,6 +27,12 @@ class WindowSource(C.Structure):
                 ("gather_base", vp), ("win_off", vp), ("win_pitch", vp)]
 
 
+class ScaledSlot(C.Structure):
+    """``rodc_scaled_slot`` (include/rodc.h)."""
+    _fields_ = [("scale", C.c_double), ("base_off", C.c_int64), ("frame_stride", C.c_int64),
+                ("width", C.c_int32), ("height", C.c_int32), ("frame_base", C.c_int32), ("individually", C.c_int32)]
+
+
 SRC_DENSE, SRC_PYRAMID, SRC_RECROP, SRC_GATHER = 0, 1, 2, 3
 IMPL_TENSOR, IMPL_SIMT = 0, 1
 
@@ -48,6 +54,11 @@ SIGNATURES = {
     "rodc_extract_windows": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "rodc_window_meta": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "rodc_window_gather_rows": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp]),
+    "rodc_window_levels": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "rodc_select_rows": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp]),
+    "rodc_plan_create_scales": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f64p, C.POINTER(vp)]),
+    "rodc_window_scaled_rows": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp]),
+    "rodc_source_windows": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]),
     "rodc_recrop": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]),
     "rodc_stage_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "rodc_stage_create_general": (C.c_int, [C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp),

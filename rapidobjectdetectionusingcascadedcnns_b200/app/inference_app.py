@@ -61,9 +61,6 @@ class InferenceApp(AbstractInferenceApp):
     @staticmethod
     def _check_supported_config():
         """Options of the reference that this path does not implement fail loudly instead of being ignored."""
-        if not cf.get("cascade_scale_patches_individually") or cf.get("cascade_scale_patches_individually_iff_not_cached"):
-            raise NotImplementedError("only cascade_scale_patches_individually=True (crop + cv2.resize per survivor, the "
-                                      "reference default, inference_cascade_app.py:363-373) is implemented")
         if cf.get("append_inception"):
             raise NotImplementedError("the Inception splice needs a network download and is out of scope")
 
@@ -186,10 +183,13 @@ class InferenceApp(AbstractInferenceApp):
                 frames.append(np.ascontiguousarray(wi.image.raw_original(True), dtype=np.uint8))
             meta[k] = (ids[key], wi.xmin_norm, wi.ymin_norm, wi.xmax_norm, wi.ymax_norm)
         raw = np.ascontiguousarray(np.asarray(windows_raw, dtype=np.uint8))
+        # Window.scale / Window.width feed the resize-then-crop branch (inference_cascade_app.py:358-359)
+        scales = np.asarray([wi.scale for wi in windows_info], np.float64)
+        widths = np.asarray([wi.width for wi in windows_info], np.int64)
         if (np.diff(meta[:, 0]) < 0).any():            # the device NMS wants candidates grouped by frame
             order = np.argsort(meta[:, 0], kind="stable")
-            meta, raw = meta[order], raw[order]
-        res = self._engine.run_windows(raw, meta, frames)
+            meta, raw, scales, widths = meta[order], raw[order], scales[order], widths[order]
+        res = self._engine.run_windows(raw, meta, frames, scales=scales, widths=widths)
         self._log_stage_stats(res)
         per_frame = self._boxes_from_result(res, infos, len(infos))
         return [b for boxes in per_frame for b in boxes]

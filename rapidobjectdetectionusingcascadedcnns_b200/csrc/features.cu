@@ -110,6 +110,44 @@ __global__ void __launch_bounds__(128) recrop_kernel(SrcDev src, int64_t n, int 
     }
 }
 
+// The u8 input of a stage for ANY window source (what the reference holds as windows_raw and feeds to X,
+// app/inference_cascade_app.py:200-202): out [n,S,S,3].  API / parity path; the stage kernels read the
+// sources in place.
+__global__ void __launch_bounds__(128) source_windows_kernel(SrcDev src, int64_t first, int64_t n, int S,
+                                                             uint8_t* __restrict__ out) {
+    extern __shared__ int tabs[];
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
+        const int64_t w = first + wrel;
+        uint8_t* o = out + wrel * (int64_t)S * S * 3;
+        if (src.kind == RODC_SRC_RECROP) {
+            __syncthreads();                                   // tables of the previous window are free
+            const Crop c = make_crop(src, w);
+            fill_recrop_tables(c, S, tabs);
+            __syncthreads();
+            for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+                int px[3];
+                recrop_pixel(c, S, tabs, i / S, i % S, px);
+                o[i * 3 + 0] = (uint8_t)px[0]; o[i * 3 + 1] = (uint8_t)px[1]; o[i * 3 + 2] = (uint8_t)px[2];
+            }
+            continue;
+        }
+        const uint8_t* p; int pitch;
+        if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
+        else if (src.kind == RODC_SRC_GATHER) { p = src.gather_base + src.win_off[w]; pitch = src.win_pitch[w]; }
+        else {
+            const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
+            const int32_t* wr = src.win + j * 8;
+            const LevelInfo& lv = src.levels[wr[0]];
+            p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
+            pitch = lv.w * 3;
+        }
+        for (int i = threadIdx.x; i < S * S * 3; i += blockDim.x) {
+            const int y = i / (S * 3), b = i - y * S * 3;
+            o[i] = p[(int64_t)y * pitch + b];
+        }
+    }
+}
+
 constexpr int FEAT_THREADS = 256;
 
 // ------------------------------------------------------------------ feature kernel, generic sizes (smem pooling)
@@ -741,6 +779,19 @@ extern "C" int rodc_recrop(const uint8_t* frames_base, const int64_t* frame_off,
     SrcDev d; memset(&d, 0, sizeof(d));
     d.kind = RODC_SRC_RECROP; d.frames_base = frames_base; d.frame_off = frame_off; d.frame_hw = frame_hw; d.meta = meta;
     recrop_kernel<<<(unsigned)n, 128, (size_t)6 * size * sizeof(int), as_stream(stream)>>>(d, n, size, out);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+extern "C" int rodc_source_windows(const rodc_window_source* src, int64_t first, int64_t n, int size, uint8_t* out,
+                                   void* stream) {
+    RODC_CHECK_ARG(src && out, "rodc_source_windows: NULL argument");
+    RODC_CHECK_ARG(size > 0 && size <= 1024 && first >= 0, "rodc_source_windows: bad size %d / first %lld", size, (long long)first);
+    if (n <= 0) return RODC_OK;
+    SrcDev d;
+    int rc = resolve_source(src, size, &d); if (rc) return rc;
+    const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
+    source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), as_stream(stream)>>>(d, first, n, size, out);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

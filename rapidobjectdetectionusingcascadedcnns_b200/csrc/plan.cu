@@ -51,6 +51,45 @@ static void pillow_coeffs(int in_size, int out_size, std::vector<int32_t>& bound
     }
 }
 
+// Places one level in the packed pyramid / scratch of a frame and appends its Pillow coefficient tables.
+static void place_level(rodc_plan* p, LevelInfo& lv, int64_t& pyr, int64_t& scr) {
+    lv.byte_off = pyr;
+    pyr += (((int64_t)lv.w * lv.h * 3) + 15) / 16 * 16;
+    lv.scratch_off = scr;
+    if (!lv.identity) {
+        scr += (((int64_t)lv.w * p->img_h * 3) + 15) / 16 * 16;
+        std::vector<int32_t> b, c; int ks = 0;
+        rodc::pillow_coeffs(p->img_w, lv.w, b, c, ks);
+        lv.kx = ks;
+        lv.hx_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
+        lv.hx_coef = (int64_t)p->tables.size();   p->tables.insert(p->tables.end(), c.begin(), c.end());
+        // dp4a form of the same coefficients: taps grouped in aligned source words of 4 pixels, every
+        // 22-bit coefficient split into three u8 limbs (exact integer arithmetic: sum = a0 + a1<<8 + a2<<16)
+        for (int xx = 0; xx < lv.w; ++xx) {
+            const int xmin = b[2 * xx], cnt = b[2 * xx + 1];
+            const int word0 = xmin >> 2, nw = ((xmin + cnt + 3) >> 2) - word0;
+            p->hitems.push_back(word0); p->hitems.push_back(nw);
+            p->hitems.push_back((int32_t)(p->hcoef.size() / 4));
+            p->hitems.push_back((int32_t)(lv.scratch_off + (int64_t)xx * 3));   // + y * w * 3 in the kernel
+            p->hitems.push_back(lv.w);
+            p->hitems.push_back(0); p->hitems.push_back(0); p->hitems.push_back(0);
+            for (int wi = 0; wi < nw; ++wi) {
+                uint32_t limb[3] = {0u, 0u, 0u};
+                for (int q = 0; q < 4; ++q) {
+                    const int x = (word0 + wi) * 4 + q, tap = x - xmin;
+                    const uint32_t cf = (tap >= 0 && tap < cnt) ? (uint32_t)c[(size_t)xx * ks + tap] : 0u;
+                    for (int l = 0; l < 3; ++l) limb[l] |= ((cf >> (8 * l)) & 0xffu) << (8 * q);
+                }
+                p->hcoef.push_back(limb[0]); p->hcoef.push_back(limb[1]); p->hcoef.push_back(limb[2]); p->hcoef.push_back(0u);
+            }
+        }
+        rodc::pillow_coeffs(p->img_h, lv.h, b, c, ks);
+        lv.ky = ks;
+        lv.vy_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
+        lv.vy_coef = (int64_t)p->tables.size();   p->tables.insert(p->tables.end(), c.begin(), c.end());
+    }
+}
+
 }  // namespace rodc
 
 using rodc::LevelInfo;
@@ -113,45 +152,48 @@ extern "C" int rodc_plan_create(int img_w, int img_h, int win, double factor, do
                 ny = col; ++nx;
             }
             lv.nx = nx; lv.ny = ny;
-            lv.byte_off = pyr;
-            pyr += (((int64_t)lv.w * lv.h * 3) + 15) / 16 * 16;
-            lv.scratch_off = scr;
-            if (!lv.identity) {
-                scr += (((int64_t)lv.w * img_h * 3) + 15) / 16 * 16;
-                std::vector<int32_t> b, c; int ks = 0;
-                rodc::pillow_coeffs(img_w, lv.w, b, c, ks);
-                lv.kx = ks;
-                lv.hx_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
-                lv.hx_coef = (int64_t)p->tables.size();   p->tables.insert(p->tables.end(), c.begin(), c.end());
-                // dp4a form of the same coefficients: taps grouped in aligned source words of 4 pixels, every
-                // 22-bit coefficient split into three u8 limbs (exact integer arithmetic: sum = a0 + a1<<8 + a2<<16)
-                for (int xx = 0; xx < lv.w; ++xx) {
-                    const int xmin = b[2 * xx], cnt = b[2 * xx + 1];
-                    const int word0 = xmin >> 2, nw = ((xmin + cnt + 3) >> 2) - word0;
-                    p->hitems.push_back(word0); p->hitems.push_back(nw);
-                    p->hitems.push_back((int32_t)(p->hcoef.size() / 4));
-                    p->hitems.push_back((int32_t)(lv.scratch_off + (int64_t)xx * 3));   // + y * w * 3 in the kernel
-                    p->hitems.push_back(lv.w);
-                    p->hitems.push_back(0); p->hitems.push_back(0); p->hitems.push_back(0);
-                    for (int wi = 0; wi < nw; ++wi) {
-                        uint32_t limb[3] = {0u, 0u, 0u};
-                        for (int q = 0; q < 4; ++q) {
-                            const int x = (word0 + wi) * 4 + q, tap = x - xmin;
-                            const uint32_t cf = (tap >= 0 && tap < cnt) ? (uint32_t)c[(size_t)xx * ks + tap] : 0u;
-                            for (int l = 0; l < 3; ++l) limb[l] |= ((cf >> (8 * l)) & 0xffu) << (8 * q);
-                        }
-                        p->hcoef.push_back(limb[0]); p->hcoef.push_back(limb[1]); p->hcoef.push_back(limb[2]); p->hcoef.push_back(0u);
-                    }
-                }
-                rodc::pillow_coeffs(img_h, lv.h, b, c, ks);
-                lv.ky = ks;
-                lv.vy_bounds = (int64_t)p->tables.size(); p->tables.insert(p->tables.end(), b.begin(), b.end());
-                lv.vy_coef = (int64_t)p->tables.size();   p->tables.insert(p->tables.end(), c.begin(), c.end());
-            }
+            rodc::place_level(p, lv, pyr, scr);
             p->levels.push_back(lv);
         }
         scale /= factor; ih /= factor; iw /= factor;            // :418-420 repeated division
         if (ih < (double)win || iw < (double)win) break;        // :423
+    }
+    if (scr >= (1ll << 31)) {
+        rodc::set_error("rodc_plan_create: horizontal-pass rows of one frame exceed 2 GiB");
+        delete p; return RODC_ERR_ARG;
+    }
+    p->pyramid_bytes = pyr > 0 ? pyr : 16;
+    p->scratch_bytes = scr > 0 ? scr : 16;
+    *out = p;
+    return RODC_OK;
+}
+
+// Pyramid of explicitly given scales, no window grid: the frames `image.raw_scaled(True, next_scale)` of the
+// reference's resize-then-crop branch (app/inference_cascade_app.py:374-394 -> data/image_info.py:201-250:
+// imresize(original, ratio) -> size (int(W*ratio), int(H*ratio)); ratio == 1.0 is the original itself).
+extern "C" int rodc_plan_create_scales(int img_w, int img_h, int n_scales, const double* scales, rodc_plan** out) {
+    RODC_CHECK_ARG(out != nullptr && (scales != nullptr || n_scales == 0), "rodc_plan_create_scales: NULL argument");
+    RODC_CHECK_ARG(img_w > 0 && img_h > 0 && n_scales >= 0, "rodc_plan_create_scales: bad sizes %dx%d, %d scales", img_w, img_h, n_scales);
+    rodc_plan* p = new (std::nothrow) rodc_plan();
+    if (!p) { rodc::set_error("out of host memory"); return RODC_ERR_NOMEM; }
+    p->img_w = img_w; p->img_h = img_h; p->win = 0; p->factor = 0.0; p->min_window_length = 0.0;
+    int64_t pyr = 0, scr = 0;
+    for (int i = 0; i < n_scales; ++i) {
+        LevelInfo lv; memset(&lv, 0, sizeof(lv));
+        lv.scale = scales[i];
+        lv.identity = (scales[i] == 1.0);
+        if (lv.identity) { lv.w = img_w; lv.h = img_h; }
+        else { lv.w = (int)((double)img_w * scales[i]); lv.h = (int)((double)img_h * scales[i]); }
+        if (!(scales[i] > 0.0) || lv.w < 1 || lv.h < 1 || lv.w > (1 << 16) || lv.h > (1 << 16)) {
+            rodc::set_error("rodc_plan_create_scales: scale %g gives a %dx%d level", scales[i], lv.w, lv.h);
+            delete p; return RODC_ERR_ARG;
+        }
+        rodc::place_level(p, lv, pyr, scr);
+        if (scr >= (1ll << 31)) {
+            rodc::set_error("rodc_plan_create_scales: horizontal-pass rows of one frame exceed 2 GiB; split the scale list");
+            delete p; return RODC_ERR_ARG;
+        }
+        p->levels.push_back(lv);
     }
     p->pyramid_bytes = pyr > 0 ? pyr : 16;
     p->scratch_bytes = scr > 0 ? scr : 16;

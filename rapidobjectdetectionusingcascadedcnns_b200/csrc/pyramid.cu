@@ -130,6 +130,47 @@ __global__ void window_gather_rows_kernel(const int32_t* __restrict__ win, const
     }
 }
 
+// Level index of every stage-0 window (+ slot_base): the key into a rodc_scaled_slot table.
+__global__ void window_levels_kernel(const int32_t* __restrict__ win, int64_t n_windows, int64_t total,
+                                     int slot_base, int32_t* __restrict__ out) {
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x)
+        out[w] = win[(w % n_windows) * 8] + slot_base;
+}
+
+// out[i] = in[idx[i]] for rows of row_words 32-bit words (survivor bookkeeping next to rodc_compact).
+__global__ void select_rows_kernel(const uint32_t* __restrict__ in, const int32_t* __restrict__ idx, int64_t n,
+                                   int row_words, uint32_t* __restrict__ out) {
+    const int64_t total = n * row_words;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / row_words; const int c = (int)(t - i * row_words);
+        out[t] = __ldg(in + (int64_t)__ldg(idx + i) * row_words + c);
+    }
+}
+
+// Resize-then-crop branch of the next-stage input (app/inference_cascade_app.py:374-394): the crop starts at
+// (int(xmin_norm * next_scale), int(ymin_norm * next_scale)) of the frame resized to next_scale and is
+// size x size; Window.raw raises ValueError when it leaves that image (data/rectangles.py:286-289) -> *err.
+__global__ void window_scaled_rows_kernel(const int32_t* __restrict__ meta, const int32_t* __restrict__ slot, int64_t n,
+                                          const rodc_scaled_slot* __restrict__ slots, int n_slots, int size,
+                                          int64_t dense_rel_off, int64_t* __restrict__ win_off,
+                                          int32_t* __restrict__ win_pitch, int32_t* __restrict__ err) {
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n; w += (int64_t)gridDim.x * blockDim.x) {
+        const int s = slot[w];
+        if (s < 0 || s >= n_slots) { atomicOr(err, 2); win_off[w] = 0; win_pitch[w] = 0; continue; }
+        const rodc_scaled_slot sl = slots[s];
+        if (sl.individually) {                 // this window keeps the crop + cv2.resize input (materialised by the caller)
+            win_off[w] = dense_rel_off + w * (int64_t)size * size * 3;
+            win_pitch[w] = size * 3;
+            continue;
+        }
+        const int32_t* m = meta + w * 5;
+        const int nx = (int)((double)m[1] * sl.scale), ny = (int)((double)m[2] * sl.scale);
+        if (nx + size > sl.width || ny + size > sl.height) { atomicOr(err, 1); win_off[w] = sl.base_off; win_pitch[w] = 0; continue; }
+        win_off[w] = sl.base_off + (int64_t)(m[0] - sl.frame_base) * sl.frame_stride + ((int64_t)ny * sl.width + nx) * 3;
+        win_pitch[w] = sl.width * 3;
+    }
+}
+
 }  // namespace rodc
 
 using namespace rodc;
@@ -203,6 +244,43 @@ extern "C" int rodc_window_gather_rows(rodc_plan* p, int n_frames, int64_t pyram
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
     window_gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, p->d_levels, N, total, pyramid_base_off,
                                                                      p->pyramid_bytes, win_off, win_pitch);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+extern "C" int rodc_window_levels(rodc_plan* p, int n_frames, int slot_base, int32_t* out, void* stream) {
+    RODC_CHECK_ARG(p && out, "rodc_window_levels: NULL argument");
+    const int64_t N = (int64_t)p->win_level.size();
+    if (n_frames <= 0 || N == 0) return RODC_OK;
+    int rc = p->ensure_device(); if (rc) return rc;
+    const int64_t total = N * n_frames;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    window_levels_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, N, total, slot_base, out);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+extern "C" int rodc_select_rows(const void* in, const int32_t* idx, int64_t n, int row_bytes, void* out, void* stream) {
+    RODC_CHECK_ARG(in && idx && out, "rodc_select_rows: NULL argument");
+    RODC_CHECK_ARG(row_bytes > 0 && (row_bytes & 3) == 0, "rodc_select_rows: row_bytes must be a positive multiple of 4 (got %d)", row_bytes);
+    if (n <= 0) return RODC_OK;
+    const int64_t total = n * (row_bytes / 4);
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    select_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(in), idx, n, row_bytes / 4,
+                                                              static_cast<uint32_t*>(out));
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
+extern "C" int rodc_window_scaled_rows(const int32_t* meta, const int32_t* slot, int64_t n, const rodc_scaled_slot* slots,
+                                       int n_slots, int size, int64_t dense_rel_off, int64_t* win_off, int32_t* win_pitch,
+                                       int32_t* err, void* stream) {
+    RODC_CHECK_ARG(meta && slot && slots && win_off && win_pitch && err, "rodc_window_scaled_rows: NULL argument");
+    RODC_CHECK_ARG(size > 0 && n_slots > 0, "rodc_window_scaled_rows: bad size %d / %d slots", size, n_slots);
+    if (n <= 0) return RODC_OK;
+    int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    window_scaled_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(meta, slot, n, slots, n_slots, size, dense_rel_off,
+                                                                     win_off, win_pitch, err);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

@@ -31,6 +31,21 @@ class GroupResult:
     trace: Optional[dict] = None     # per-stage device tensors when requested (tests)
 
 
+@dataclass
+class WindowOrigin:
+    """Where the stage-0 windows of a run live, for the two next-stage input rules that do not re-crop
+    from the original frame (`app/inference_cascade_app.py:234-240,374-394`).
+
+    ``gather``: closure -> ``(base, win_off [n0] i64, win_pitch [n0] i32)`` addressing every stage-0 window
+    (cascades whose stages share one input size keep the SAME raw windows).
+    ``slot`` / ``groups``: per stage-0 window the index of its (frame group, pyramid level) and, per group,
+    ``dict(frames=[n,H,W,3] u8 CUDA, frame_base, scales=float64 [L], width)`` -- the resize-then-crop
+    branch (``cascade_scale_patches_individually=False``) resizes whole frames to ``scale * size / width``."""
+    gather: Optional[object] = None
+    slot: Optional[torch.Tensor] = None
+    groups: Optional[List[dict]] = None
+
+
 class CascadeEngine:
     """Runs a list of ``native.Stage`` over frame batches.  ``single=True`` applies the
     single-net decision rule (argmax != background, confidence = p[argmax])."""
@@ -46,6 +61,7 @@ class CascadeEngine:
         self.single = single
         self.sizes = [s.in_size for s in self.stages]
         self._plans: Dict[Tuple, native.Plan] = {}
+        self._scaled_plans: Dict[Tuple, native.Plan] = {}
         self._ws: Optional[torch.Tensor] = None
         self.kernel_launches = 0        # launches of OUR kernels (bench.py reports it)
 
@@ -57,6 +73,83 @@ class CascadeEngine:
             p = native.Plan(*key)
             self._plans[key] = p
         return p
+
+    def scaled_plan_for(self, w: int, h: int, scales: Tuple[float, ...]) -> native.Plan:
+        key = (w, h, scales)
+        p = self._scaled_plans.get(key)
+        if p is None:
+            if len(self._scaled_plans) > 64:
+                self._scaled_plans.clear()
+            p = native.Plan.from_scales(w, h, scales)
+            self._scaled_plans[key] = p
+        return p
+
+    @property
+    def increasing_dims(self) -> bool:
+        """`app/inference_cascade_app.py:403-420`: first stage input narrower than the last one."""
+        return self.sizes[0] < self.sizes[-1]
+
+    @staticmethod
+    def _scaled_branch_possible() -> bool:
+        """True when some survivor may take the resize-then-crop branch (`:362-365`)."""
+        return (not cf.get("cascade_scale_patches_individually")) or \
+            bool(cf.get("cascade_scale_patches_individually_iff_not_cached"))
+
+    def _scaled_source(self, origin: WindowOrigin, size: int, meta: torch.Tensor, slot: torch.Tensor, n: int,
+                       table: native.FrameTable):
+        """Next-stage input by resize-then-crop (`app/inference_cascade_app.py:374-394`): build the frames
+        ``raw_scaled(next_scale)`` of every (group, level) that takes the branch (K1 on an explicit scale list)
+        and address the survivors' ``size x size`` crops as GATHER rows.  Returns ``None`` when no level takes
+        the branch (``..._iff_not_cached`` with nothing cached: every survivor is cropped individually)."""
+        individually = bool(cf.get("cascade_scale_patches_individually"))
+        per_group, total, any_scaled, any_individual = [], 0, False, False
+        for g in origin.groups:
+            # next_scale = window.scale * (cf img_width / window.width)                       (`:358-359`)
+            ns = np.asarray(g["scales"], np.float64) * (size / np.asarray(g["width"], np.float64))
+            # is_raw_scaled_cached(next_scale): the per-image cache holds the levels the stage-0 extraction
+            # touched, keyed by the scale's repr; scale 1.0 is never stored under such a key
+            # (`data/image_info.py:201-213,252-258`)
+            cached = {float(v) for v in np.asarray(g["scales"], np.float64).tolist() if float(v) != 1.0}
+            use = [(not individually) or (float(v) in cached) for v in ns.tolist()]
+            sel = [k for k, u in enumerate(use) if u]
+            any_scaled |= bool(sel); any_individual |= len(sel) < len(use)
+            fr = g["frames"]
+            plan2 = self.scaled_plan_for(int(fr.shape[2]), int(fr.shape[1]), tuple(float(ns[k]) for k in sel)) if sel else None
+            per_group.append((g, ns, sel, plan2, total))
+            if plan2 is not None:
+                total += int(fr.shape[0]) * plan2.pyramid_bytes
+        if not any_scaled:
+            return None
+        buf = torch.empty((max(total, 16),), dtype=torch.uint8, device=self.device)
+        entries = []
+        for g, ns, sel, plan2, base in per_group:
+            fr = g["frames"]; nf = int(fr.shape[0])
+            pos = {k: j for j, k in enumerate(sel)}
+            if plan2 is not None:
+                native.pyramid(plan2, fr, out=buf[base:base + nf * plan2.pyramid_bytes].view(nf, plan2.pyramid_bytes))
+                self.kernel_launches += 2
+            for k in range(len(ns)):
+                if k in pos:
+                    j = pos[k]
+                    entries.append((float(ns[k]), base + int(plan2.byte_offset[j]), plan2.pyramid_bytes if nf > 1 else 0,
+                                    int(plan2.level_w[j]), int(plan2.level_h[j]), int(g["frame_base"]), 0))
+                else:
+                    entries.append((float(ns[k]), 0, 0, 0, 0, int(g["frame_base"]), 1))
+        slots = native.scaled_slots(entries, self.device)
+        dense, rel = None, 0
+        if any_individual:                    # mixed: those survivors keep the crop + cv2.resize input (K4, materialised)
+            dense = native.recrop(table, meta[:n], size)
+            rel = dense.data_ptr() - buf.data_ptr()
+            self.kernel_launches += 1
+        win_off, win_pitch, err = native.window_scaled_rows(meta, slot, n, slots, len(entries), size, rel)
+        self.kernel_launches += 1
+        flags = int(err.item())
+        if flags & 1:
+            raise ValueError("ymax/xmax must not leave the image boundaries")      # `data/rectangles.py:286-289`
+        if flags:
+            raise native._lib.RodcError("rodc_window_scaled_rows: bad level slot")
+        self._keepalive2 = (buf, slots, dense, win_off, win_pitch)
+        return native.make_source(gather_base=buf, win_off=win_off, win_pitch=win_pitch)
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
@@ -85,7 +178,7 @@ class CascadeEngine:
 
     # ------------------------------------------------------------------ stages on a window set
     def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
-                    keep_trace: bool) -> GroupResult:
+                    keep_trace: bool, origin: Optional[WindowOrigin] = None) -> GroupResult:
         dev = self.device
         impl = self._impl()
         n_st = len(self.stages)
@@ -94,16 +187,24 @@ class CascadeEngine:
                      cf.FINAL_CONFIDENCE_CALCULATION_AVG: native.CONF_AVG,
                      cf.FINAL_CONFIDENCE_CALCULATION_MULT: native.CONF_MULT}[mode_key]
         res = GroupResult(np.zeros((0, 4), np.int32), np.zeros((0,), np.float32), np.zeros((0,), np.int32), n_windows=n0)
-        trace = {"probs": [], "logits": [], "keep": [], "meta": []} if keep_trace else None
+        trace = {"probs": [], "logits": [], "keep": [], "meta": [], "X": []} if keep_trace else None
         n, meta, src = n0, meta0, src0
         bott = torch.empty((n, self.stages[0].width), dtype=torch.float32, device=dev)
         conf_acc = None
+        same_windows = n_st > 1 and not self.increasing_dims          # `:234-240`: the raw windows are kept
+        scaled = n_st > 1 and self.increasing_dims and self._scaled_branch_possible()
+        if (same_windows or scaled) and origin is None:
+            raise ValueError("this cascade configuration needs the origin of the stage-0 windows")
+        rows = origin.gather() if same_windows else None            # (base, win_off, win_pitch) of the live windows
+        slot = origin.slot if scaled else None
         for i, st in enumerate(self.stages):
             if n < 1:
                 break                                                       # inference_cascade_app.py:140-142
             last = i == n_st - 1
             ws_bytes = st.workspace_bytes(n, impl)
             ws = self._workspace(ws_bytes)
+            if keep_trace:                      # the stage's u8 input, i.e. the reference's windows_raw (tests)
+                trace["X"].append(native.source_windows(src, 0, n, st.in_size, dev))
             logits, probs = native.stage_forward(st, src, 0, n, bott, ws[:ws_bytes], impl)
             self._count_stage_launches(st, n, ws_bytes)
             # single net: keep argmax != background <=> p[1] > p[0] <=> p[1] > 0.5 (ties -> background,
@@ -126,13 +227,25 @@ class CascadeEngine:
                 trace["probs"].append(probs); trace["logits"].append(logits); trace["keep"].append(keep[:kept].clone())
                 trace["meta"].append(meta)
             meta, n = meta_out, kept
-            if not last:
+            if not last and kept > 0:
                 bott = bott_next
-                src = native.make_source(table=table, meta=meta)
-                self._keepalive = (table, meta)
+                src = None
+                if same_windows:
+                    # the reference appends windows_raw[window_index_original] only next to the bottleneck copy
+                    # (`:234-237`); without reuse_bottlenecks it would feed an empty array -- the windows are kept here too
+                    rows = (rows[0], native.select_rows(rows[1], keep, kept), native.select_rows(rows[2], keep, kept))
+                    self.kernel_launches += 2
+                    src = native.make_source(gather_base=rows[0], win_off=rows[1], win_pitch=rows[2])
+                elif scaled:
+                    slot = native.select_rows(slot, keep, kept)
+                    self.kernel_launches += 1
+                    src = self._scaled_source(origin, nxt.in_size, meta, slot, kept, table)
+                if src is None:
+                    src = native.make_source(table=table, meta=meta)
+                self._keepalive = (table, meta, rows, slot)
                 if mode_key != cf.FINAL_CONFIDENCE_CALCULATION_LAST_STEP:
                     conf_acc = conf_out
-            else:
+            elif last:
                 final_conf = conf_out[:kept]
                 if mode_key == cf.FINAL_CONFIDENCE_CALCULATION_AVG:
                     final_conf = final_conf / np.float32(n_st)
@@ -210,7 +323,20 @@ class CascadeEngine:
             self.kernel_launches += 1
             table = native.FrameTable.from_batch(frames)
             src0 = native.make_source(plan=plan, pyr=pyr)
-            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace)
+            origin = None
+            if len(self.stages) > 1 and not self.increasing_dims:
+                def _rows():
+                    off = torch.empty((n * plan.n_windows,), dtype=torch.int64, device=self.device)
+                    pitch = torch.empty((n * plan.n_windows,), dtype=torch.int32, device=self.device)
+                    native.window_gather_rows(plan, n, 0, off, pitch)
+                    self.kernel_launches += 1
+                    return pyr, off, pitch
+                origin = WindowOrigin(gather=_rows)
+            elif len(self.stages) > 1 and self._scaled_branch_possible():
+                origin = WindowOrigin(slot=native.window_levels(plan, n, 0, self.device),
+                                      groups=[dict(frames=frames, frame_base=0, scales=plan.scale, width=plan.win)])
+                self.kernel_launches += 1
+            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, origin)
 
     def run_mixed(self, frames: Sequence[np.ndarray], keep_trace: bool = False) -> Tuple[GroupResult, List[int]]:
         """Whole path for host frames of DIFFERENT shapes in one set of stage launches (the reference's
@@ -250,7 +376,10 @@ class CascadeEngine:
             win_off = torch.empty((n_windows,), dtype=torch.int64, device=self.device)
             win_pitch = torch.empty((n_windows,), dtype=torch.int32, device=self.device)
             meta0 = torch.empty((n_windows, 5), dtype=torch.int32, device=self.device)
-            fbase = wbase = pbase = 0
+            want_slots = len(self.stages) > 1 and self.increasing_dims and self._scaled_branch_possible()
+            slot0 = torch.empty((n_windows,), dtype=torch.int32, device=self.device) if want_slots else None
+            slot_groups: List[dict] = []
+            fbase = wbase = pbase = sbase = 0
             pos = 0
             for k, idx in groups.items():
                 p, n = plans[k], len(idx)
@@ -264,22 +393,63 @@ class CascadeEngine:
                 _l.check(_l.lib().rodc_window_meta(p.handle, n, fbase, C.c_void_p(meta0[wbase:wbase + nw].data_ptr()),
                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rodc_window_meta")
                 self.kernel_launches += 4
+                if want_slots:
+                    _l.check(_l.lib().rodc_window_levels(p.handle, n, sbase, C.c_void_p(slot0[wbase:wbase + nw].data_ptr()),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rodc_window_levels")
+                    self.kernel_launches += 1
+                    slot_groups.append(dict(frames=d, frame_base=fbase, scales=p.scale, width=p.win))
+                    sbase += p.n_levels
                 fbase += n; wbase += nw; pbase += n * p.pyramid_bytes; pos += n
             src0 = native.make_source(gather_base=pyr, win_off=win_off, win_pitch=win_pitch)
             self._keepalive0 = (pyr, win_off, win_pitch, flat, table)
-            return self._run_stages(src0, n_windows, meta0, table, len(order), keep_trace), order
+            origin = WindowOrigin(gather=lambda: (pyr, win_off, win_pitch), slot=slot0, groups=slot_groups)
+            return self._run_stages(src0, n_windows, meta0, table, len(order), keep_trace, origin), order
 
-    def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False) -> GroupResult:
+    def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False,
+                    scales: Optional[np.ndarray] = None, widths: Optional[np.ndarray] = None) -> GroupResult:
         """``run_inference_on_windows``: caller-extracted stage-0 windows ``[n,S,S,3]`` u8 plus their
         metadata rows ``(frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm)``; ``frames`` are the
-        original images the later stages re-crop from."""
+        original images the later stages re-crop from.  ``scales`` / ``widths`` (``Window.scale`` and
+        ``Window.width`` per window) are needed only by the resize-then-crop branch."""
         with torch.cuda.device(self.device):
             wr = torch.from_numpy(np.ascontiguousarray(windows_raw, np.uint8)).to(self.device)
             m = torch.from_numpy(np.ascontiguousarray(meta, np.int32)).to(self.device)
-            table = native.FrameTable.from_list([torch.from_numpy(np.ascontiguousarray(f)).to(self.device) for f in frames])
+            dev_frames = [torch.from_numpy(np.ascontiguousarray(f)).to(self.device) for f in frames]
+            table = native.FrameTable.from_list(dev_frames)
             src0 = native.make_source(dense=wr)
             self._keepalive0 = (wr, m, table)
-            return self._run_stages(src0, int(wr.shape[0]), m, table, len(frames), keep_trace)
+            n0, S = int(wr.shape[0]), int(wr.shape[1])
+            origin = None
+            if len(self.stages) > 1 and not self.increasing_dims:
+                origin = WindowOrigin(gather=lambda: (
+                    wr, torch.arange(n0, dtype=torch.int64, device=self.device) * (S * S * 3),
+                    torch.full((n0,), S * 3, dtype=torch.int32, device=self.device)))
+            elif len(self.stages) > 1 and self._scaled_branch_possible():
+                if scales is None or widths is None:
+                    raise ValueError("the resize-then-crop branch needs Window.scale and Window.width of every window")
+                # one slot per distinct (frame, scale, width), one group per frame
+                per_frame: Dict[int, List[Tuple[float, int]]] = {}
+                slot_of = np.empty((n0,), np.int32)
+                fids = np.asarray(meta)[:, 0].tolist()
+                order_frames: List[int] = []
+                for f in fids:
+                    if f not in per_frame:
+                        per_frame[f] = []; order_frames.append(f)
+                local: Dict[Tuple[int, float, int], int] = {}
+                for i, (f, sc, wd) in enumerate(zip(fids, np.asarray(scales, np.float64).tolist(), np.asarray(widths).tolist())):
+                    k = (f, sc, int(wd))
+                    if k not in local:
+                        local[k] = len(per_frame[f]); per_frame[f].append((sc, int(wd)))
+                bases, b = {}, 0
+                for f in order_frames:
+                    bases[f] = b; b += len(per_frame[f])
+                for i, (f, sc, wd) in enumerate(zip(fids, np.asarray(scales, np.float64).tolist(), np.asarray(widths).tolist())):
+                    slot_of[i] = bases[f] + local[(f, sc, int(wd))]
+                groups = [dict(frames=dev_frames[f].view(1, *dev_frames[f].shape), frame_base=f,
+                               scales=np.asarray([v[0] for v in per_frame[f]], np.float64),
+                               width=np.asarray([v[1] for v in per_frame[f]], np.float64)) for f in order_frames]
+                origin = WindowOrigin(slot=torch.from_numpy(slot_of).to(self.device), groups=groups)
+            return self._run_stages(src0, n0, m, table, len(frames), keep_trace, origin)
 
     def softmax_on_raw(self, raw: np.ndarray) -> np.ndarray:
         """``run_inference_on_raw_data`` of the single net: softmax ``[n,2]`` for dense windows."""

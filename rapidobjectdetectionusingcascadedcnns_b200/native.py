@@ -49,6 +49,25 @@ class Plan:
         self._h = h
         self.img_w, self.img_h, self.win = int(img_w), int(img_h), int(win)
         self.factor, self.min_window_length = float(factor), float(min_window_length)
+        self._read()
+
+    @classmethod
+    def from_scales(cls, img_w: int, img_h: int, scales: Sequence[float]) -> "Plan":
+        """Pyramid of explicit scales without a window grid: the frames ``image.raw_scaled(True, next_scale)``
+        of the resize-then-crop branch (`app/inference_cascade_app.py:374-394`)."""
+        self = cls.__new__(cls)
+        sc = np.ascontiguousarray(scales, np.float64)
+        h = C.c_void_p()
+        check(_lib.lib().rodc_plan_create_scales(int(img_w), int(img_h), int(sc.shape[0]), sc.ctypes.data_as(_lib.c_f64p),
+                                                 C.byref(h)), "rodc_plan_create_scales")
+        self._h = h
+        self.img_w, self.img_h, self.win = int(img_w), int(img_h), 0
+        self.factor, self.min_window_length = 0.0, 0.0
+        self._read()
+        return self
+
+    def _read(self):
+        L, h = _lib.lib(), self._h
         self.n_levels = L.rodc_plan_n_levels(h)
         self.n_windows = int(L.rodc_plan_n_windows(h))
         self.fits = bool(L.rodc_plan_fits(h))
@@ -130,6 +149,48 @@ def window_gather_rows(plan: Plan, n_frames: int, pyramid_base_off: int, win_off
     _require_cuda(win_off, win_pitch)
     check(_lib.lib().rodc_window_gather_rows(plan.handle, int(n_frames), int(pyramid_base_off), _ptr(win_off), _ptr(win_pitch),
                                              _stream()), "rodc_window_gather_rows")
+
+
+def window_levels(plan: Plan, n_frames: int, slot_base: int, device) -> torch.Tensor:
+    """Level index (+ ``slot_base``) of every stage-0 window of ``n_frames`` frames, ``[n_frames*N]`` i32."""
+    out = torch.empty((n_frames * plan.n_windows,), dtype=torch.int32, device=device)
+    with torch.cuda.device(out.device):
+        check(_lib.lib().rodc_window_levels(plan.handle, int(n_frames), int(slot_base), _ptr(out), _stream()), "rodc_window_levels")
+    return out
+
+
+def select_rows(src: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    """``src[idx[:n]]`` for small per-window records (rows of a multiple of 4 bytes), done by librodc."""
+    _require_cuda(src, idx)
+    assert src.is_contiguous() and idx.dtype == torch.int32
+    row_bytes = src.element_size() * (src[0].numel() if src.dim() > 1 else 1)
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    check(_lib.lib().rodc_select_rows(_ptr(src), _ptr(idx), int(n), int(row_bytes), _ptr(out), _stream()), "rodc_select_rows")
+    return out
+
+
+def scaled_slots(entries: Sequence[Tuple[float, int, int, int, int, int, int]], device) -> torch.Tensor:
+    """Device copy of a ``rodc_scaled_slot`` table from ``(scale, base_off, frame_stride, width, height,
+    frame_base, individually)`` tuples."""
+    arr = (_lib.ScaledSlot * max(len(entries), 1))()
+    for i, e in enumerate(entries):
+        arr[i] = _lib.ScaledSlot(float(e[0]), int(e[1]), int(e[2]), int(e[3]), int(e[4]), int(e[5]), int(e[6]))
+    host = np.frombuffer(arr, dtype=np.uint8).copy()
+    return torch.from_numpy(host).to(device)
+
+
+def window_scaled_rows(meta: torch.Tensor, slot: torch.Tensor, n: int, slots: torch.Tensor, n_slots: int, size: int,
+                       dense_rel_off: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """GATHER rows of the resize-then-crop branch; returns ``(win_off, win_pitch, err)`` (``err`` is a device
+    i32: bit 0 = a crop leaves its resized frame, the reference's ``Window.raw`` ValueError)."""
+    _require_cuda(meta, slot, slots)
+    win_off = torch.empty((n,), dtype=torch.int64, device=meta.device)
+    win_pitch = torch.empty((n,), dtype=torch.int32, device=meta.device)
+    err = torch.zeros((1,), dtype=torch.int32, device=meta.device)
+    check(_lib.lib().rodc_window_scaled_rows(_ptr(meta), _ptr(slot), int(n), _ptr(slots), int(n_slots), int(size),
+                                             int(dense_rel_off), _ptr(win_off), _ptr(win_pitch), _ptr(err), _stream()),
+          "rodc_window_scaled_rows")
+    return win_off, win_pitch, err
 
 
 class FrameTable:
@@ -267,6 +328,13 @@ def stage_forward(stage: Stage, src: WindowSource, first: int, n: int, bottlenec
                                         int(workspace.numel() * workspace.element_size()), int(impl), _stream()),
           "rodc_stage_forward")
     return logits, probs
+
+
+def source_windows(src: WindowSource, first: int, n: int, size: int, device) -> torch.Tensor:
+    """The u8 stage input ``[n,size,size,3]`` of any window source (the reference's ``windows_raw``)."""
+    out = torch.empty((n, size, size, 3), dtype=torch.uint8, device=device)
+    check(_lib.lib().rodc_source_windows(C.byref(src), int(first), int(n), int(size), _ptr(out), _stream()), "rodc_source_windows")
+    return out
 
 
 def stage_features(stage: Stage, src: WindowSource, first: int, n: int, device) -> torch.Tensor:

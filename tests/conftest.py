@@ -26,6 +26,9 @@ def load_golden(name):
 
 CASCADE_CASES = ["cascade_small", "cascade_small_reject", "cascade_640x480", "cascade_factor12_enlarge",
                  "cascade_conf_avg", "cascade_conf_mult"]
+# reference options off by default: resize-then-crop next-stage input, its ..._iff_not_cached variant
+# (window_scale_factor 2 so that both branches are taken), one input size for all stages
+OPTION_CASES = ["cascade_scaled_patches", "cascade_iff_not_cached", "cascade_equal_dims"]
 
 
 def case_inputs(name):
@@ -37,6 +40,8 @@ def case_inputs(name):
     frames = [synth.synth_frame(h, w, s) for (h, w, s) in meta["frames"]]
     if meta["single"]:
         weights = [synth.xavier_stage_weights(2, 48)]
+    elif meta.get("sizes"):
+        weights = [synth.xavier_stage_weights(i, sz, n_prev_bottleneck=512 * i) for i, sz in enumerate(meta["sizes"])]
     else:
         weights = synth.xavier_cascade()
     for w, o in zip(weights, meta["offsets"]):

@@ -10,12 +10,17 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import CASCADE_CASES, case_inputs
+from conftest import CASCADE_CASES, OPTION_CASES, case_inputs
 
 pytestmark = pytest.mark.gpu
 
 # epsilon band on the logit margin, per stage: fp32 accumulation noise grows ~sqrt(K)
 EPS = [1e-4, 2e-4, 4e-4]
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def _set_cf(pkg, meta_cf):
@@ -36,7 +41,7 @@ def pkg():
 
 
 @pytest.mark.parametrize("impl", ["tensor", "simt"])
-@pytest.mark.parametrize("name", CASCADE_CASES)
+@pytest.mark.parametrize("name", CASCADE_CASES + OPTION_CASES)
 def test_cascade_app_matches_reference_run(pkg, name, impl):
     from oracle import cascade as oc
     g, frames, weights, ocfg = case_inputs(name)
@@ -57,7 +62,10 @@ def test_cascade_app_matches_reference_run(pkg, name, impl):
         shapes.setdefault(f.shape, []).append(fi)
     if len(shapes) == 1:
         res = eng.run_frames(np.stack(frames), keep_trace=True)
-        assert res.stage_in == [s.n_in for s in r64.stages][:len(res.stage_in)] or True
+    else:
+        res, order = eng.run_mixed(frames, keep_trace=True)
+        assert order == list(range(len(frames)))       # shape groups happen to be in input order in the golden cases
+    if True:
         n_checked = 0
         prev_equal = True
         for i, st in enumerate(r64.stages):
@@ -66,6 +74,9 @@ def test_cascade_app_matches_reference_run(pkg, name, impl):
             keep_gpu = res.trace["keep"][i].cpu().numpy()
             lg = res.trace["logits"][i].cpu().numpy().astype(np.float64)
             assert lg.shape == st.logits.shape
+            # the u8 input of the stage is the array the REFERENCE fed to X in its own run (pyramid crops,
+            # cv2.resize re-crops, resize-then-crop patches or the carried raw windows), bit for bit
+            assert _sha(res.trace["X"][i].cpu().numpy()) == str(g["stage%d_X_sha" % i]), "stage %d input differs" % i
             rel = np.abs(lg - st.logits).max() / np.abs(st.logits).max()
             assert rel < 1e-3, "stage %d logits off by %g relative" % (i, rel)
             np.testing.assert_allclose(res.trace["probs"][i].cpu().numpy(), st.probs, rtol=1e-3, atol=1e-6)
@@ -124,19 +135,23 @@ def test_single_net_app_matches_reference_run(pkg):
                                 ).run_inference_on_raw_data(raw[:2])
 
 
-def test_run_inference_on_windows_entry_point(pkg):
-    """Caller-extracted windows (reference ``Window`` semantics) give the same boxes as the image path."""
+@pytest.mark.parametrize("name", ["cascade_small_reject"] + OPTION_CASES)
+def test_run_inference_on_windows_entry_point(pkg, name):
+    """Caller-extracted windows (reference ``Window`` semantics) give the same boxes as the image path, also
+    for the next-stage input rules that need ``Window.scale`` (resize-then-crop) or the raw windows themselves."""
     from oracle import cascade as oc, plan as oplan
-    g, frames, weights, ocfg = case_inputs("cascade_small_reject")
+    g, frames, weights, ocfg = case_inputs(name)
     _set_cf(pkg, g["meta"]["cf"])
-    app = pkg.InferenceCascadeApp("w", stage_models=[pkg.StageModel(w) for w in weights])
+    models = [pkg.StageModel(w) for w in weights]
+    app = pkg.InferenceCascadeApp("w", stage_models=models)
     infos = _infos(pkg, frames, "win")
     winfo, raws = [], []
+    s0 = models[0].in_size
     for info, fr in zip(infos, frames):
-        raw, p = oc.extract_windows(fr, 12, ocfg)
+        raw, p = oc.extract_windows(fr, s0, ocfg)
         raws.append(raw)
         for k in range(p.n_windows):
-            winfo.append(pkg.Window(int(p.win_x[k]), int(p.win_y[k]), int(p.win_x[k]) + 12, int(p.win_y[k]) + 12,
+            winfo.append(pkg.Window(int(p.win_x[k]), int(p.win_y[k]), int(p.win_x[k]) + s0, int(p.win_y[k]) + s0,
                                     info, p.levels[p.win_level[k]].scale))
     boxes = app.run_inference_on_windows(winfo, np.concatenate(raws))
     ref = app.run_inference_on_images(infos, merge=True)
@@ -231,7 +246,7 @@ def test_extract_windows_entry_points(pkg):
     assert np.array_equal(np.asarray(rows, np.int32), g["win_table"])
     assert np.array_equal(np.asarray(scales), g["win_scale"])
     assert app._extract_windows(pkg.ArrayImageInfo(np.zeros((6, 6, 3), np.uint8), "tiny.png")) == ([], [])
-    pkg.cf.set("cascade_scale_patches_individually", False)
+    pkg.cf.set("append_inception", True)
     with pytest.raises(NotImplementedError):
         pkg.InferenceCascadeApp("y", stage_models=[pkg.StageModel(w) for w in weights]).run_inference_on_images([])
 

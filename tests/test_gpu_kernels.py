@@ -32,6 +32,72 @@ def dev(a):
 
 
 # ------------------------------------------------------------------ K1 pyramid + windows
+
+def test_scaled_plan_pyramid_bit_exact_incl_upscaling(nat):
+    """rodc_plan_create_scales + rodc_pyramid = image.raw_scaled(next_scale) of the resize-then-crop branch
+    (app/inference_cascade_app.py:374-394): Pillow BILINEAR to (int(W*s), int(H*s)), down- AND up-scaling,
+    scale 1.0 = the frame itself; against the oracle's integer Pillow restatement and the installed Pillow."""
+    from PIL import Image
+    from oracle import cascade as oc
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    frames = np.stack([synth.synth_frame(61, 83, 40 + s) for s in range(3)])
+    scales = [0.9576, 1.0, 0.5, 0.2393920493, 1.9152, 2.0, 3.3, 0.0625]
+    plan = nat.Plan.from_scales(83, 61, scales)
+    assert plan.n_levels == len(scales) and plan.n_windows == 0
+    pyr = nat.pyramid(plan, dev(frames))
+    for f in range(3):
+        cache = oc.ScaledCache(frames[f], "restated")
+        for l, sc in enumerate(scales):
+            got = nat.pyramid_level(plan, pyr, f, l).cpu().numpy()
+            ref = cache.raw_scaled(sc)
+            assert got.shape == ref.shape == (61, 83, 3) if sc == 1.0 else got.shape == (int(61 * sc), int(83 * sc), 3)
+            assert np.array_equal(got, ref), "frame %d scale %g differs from the restatement" % (f, sc)
+            if sc != 1.0:
+                lib = np.asarray(Image.fromarray(frames[f]).resize((int(83 * sc), int(61 * sc)), resample=2))
+                assert np.array_equal(got, lib), "frame %d scale %g differs from Pillow" % (f, sc)
+
+
+def test_window_scaled_rows_and_select_rows(nat):
+    """GATHER rows of the resize-then-crop branch: int(xmin_norm * next_scale) truncation, frame stride, the
+    Window.raw bounds flag, the per-window 'individually' escape; rodc_select_rows = fancy indexing."""
+    rs = np.random.RandomState(5)
+    entries = [(0.47878, 1000, 5000, 76, 57, 0, 0), (0.957584, 40000, 70000, 153, 114, 2, 0), (1.0, 0, 0, 0, 0, 0, 1)]
+    slots = nat.scaled_slots(entries, torch.device("cuda"))
+    n, size = 500, 24
+    slot = rs.randint(0, 3, n).astype(np.int32)
+    meta = np.zeros((n, 5), np.int32)
+    meta[:, 0] = np.where(slot == 1, rs.randint(2, 5, n), rs.randint(0, 2, n))
+    meta[:, 1] = rs.randint(0, 120, n); meta[:, 2] = rs.randint(0, 80, n)
+    off, pitch, err = nat.window_scaled_rows(dev(meta), dev(slot), n, slots, 3, size, dense_rel_off=-12345)
+    off, pitch = off.cpu().numpy(), pitch.cpu().numpy()
+    bad = False
+    for i in range(n):
+        sc, base, stride, w, h, fb, ind = entries[slot[i]]
+        if ind:
+            assert off[i] == -12345 + i * size * size * 3 and pitch[i] == size * 3
+            continue
+        nx, ny = int(int(meta[i, 1]) * sc), int(int(meta[i, 2]) * sc)
+        if nx + size > w or ny + size > h:
+            bad = True
+            continue
+        assert off[i] == base + (meta[i, 0] - fb) * stride + (ny * w + nx) * 3, i
+        assert pitch[i] == w * 3
+    assert bad and int(err.item()) == 1
+    ok = (slot == 2)
+    _, _, err2 = nat.window_scaled_rows(dev(meta[ok]), dev(slot[ok]), int(ok.sum()), slots, 3, size)
+    assert int(err2.item()) == 0
+    _, _, err3 = nat.window_scaled_rows(dev(meta[:4]), dev(np.full(4, 7, np.int32)), 4, slots, 3, size)
+    assert int(err3.item()) == 2
+    src = rs.randint(-1000, 1000, (300, 5)).astype(np.int32)
+    idx = rs.randint(0, 300, 1234).astype(np.int32)
+    assert np.array_equal(nat.select_rows(dev(src), dev(idx), 1234).cpu().numpy(), src[idx])
+    src64 = rs.randint(-2 ** 40, 2 ** 40, 300).astype(np.int64)
+    assert np.array_equal(nat.select_rows(dev(src64), dev(idx), 1000).cpu().numpy(), src64[idx[:1000]])
+    plan = nat.Plan(160, 120, 12, 1.1, 0.2)
+    lv = nat.window_levels(plan, 3, 10, torch.device("cuda")).cpu().numpy()
+    assert np.array_equal(lv, np.tile(plan.win_level, 3) + 10)
+
+
 @pytest.mark.parametrize("name", ["cascade_small", "cascade_640x480", "cascade_factor12_enlarge"])
 def test_pyramid_and_windows_bit_exact(nat, name):
     from oracle import cascade as oc, plan as oplan
