@@ -388,14 +388,10 @@ class CascadeEngine:
                 native.pyramid(p, d, out=pyr[pbase:pbase + n * p.pyramid_bytes].view(n, p.pyramid_bytes))
                 nw = n * p.n_windows
                 native.window_gather_rows(p, n, pbase, win_off[wbase:wbase + nw], win_pitch[wbase:wbase + nw])
-                from . import _lib as _l
-                import ctypes as C
-                _l.check(_l.lib().rodc_window_meta(p.handle, n, fbase, C.c_void_p(meta0[wbase:wbase + nw].data_ptr()),
-                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rodc_window_meta")
+                native.window_meta(p, n, fbase, self.device, out=meta0[wbase:wbase + nw])
                 self.kernel_launches += 4
                 if want_slots:
-                    _l.check(_l.lib().rodc_window_levels(p.handle, n, sbase, C.c_void_p(slot0[wbase:wbase + nw].data_ptr()),
-                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rodc_window_levels")
+                    native.window_levels(p, n, sbase, self.device, out=slot0[wbase:wbase + nw])
                     self.kernel_launches += 1
                     slot_groups.append(dict(frames=d, frame_base=fbase, scales=p.scale, width=p.win))
                     sbase += p.n_levels

@@ -136,8 +136,11 @@ def extract_windows(plan: Plan, pyr: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def window_meta(plan: Plan, n_frames: int, frame_id_base: int, device) -> torch.Tensor:
-    out = torch.empty((n_frames * plan.n_windows, 5), dtype=torch.int32, device=device)
+def window_meta(plan: Plan, n_frames: int, frame_id_base: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Rows ``(frame_id, xmin_norm, ymin_norm, xmax_norm, ymax_norm)`` of every stage-0 window (optionally into ``out``)."""
+    if out is None:
+        out = torch.empty((n_frames * plan.n_windows, 5), dtype=torch.int32, device=device)
+    assert out.is_contiguous() and out.numel() == n_frames * plan.n_windows * 5
     with torch.cuda.device(out.device):
         check(_lib.lib().rodc_window_meta(plan.handle, n_frames, frame_id_base, _ptr(out), _stream()), "rodc_window_meta")
     return out
@@ -151,9 +154,11 @@ def window_gather_rows(plan: Plan, n_frames: int, pyramid_base_off: int, win_off
                                              _stream()), "rodc_window_gather_rows")
 
 
-def window_levels(plan: Plan, n_frames: int, slot_base: int, device) -> torch.Tensor:
+def window_levels(plan: Plan, n_frames: int, slot_base: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Level index (+ ``slot_base``) of every stage-0 window of ``n_frames`` frames, ``[n_frames*N]`` i32."""
-    out = torch.empty((n_frames * plan.n_windows,), dtype=torch.int32, device=device)
+    if out is None:
+        out = torch.empty((n_frames * plan.n_windows,), dtype=torch.int32, device=device)
+    assert out.is_contiguous() and out.numel() == n_frames * plan.n_windows
     with torch.cuda.device(out.device):
         check(_lib.lib().rodc_window_levels(plan.handle, int(n_frames), int(slot_base), _ptr(out), _stream()), "rodc_window_levels")
     return out
