@@ -24,15 +24,28 @@
 namespace rodc {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int FC1_N = 512;                          // fc1 width the tensor path is built for
 constexpr int UMMA_K = 16;
 constexpr int A_TILE = BM * BK * 2;                 // 16 KB
-constexpr int B_TILE = BN * BK * 2;                 // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr int TMEM_COLS = 512;                 // two 128 x 256 fp32 accumulator buffers
+constexpr int TMEM_COLS = 512;                 // two 128 x 256 fp32 accumulator buffers (2-CTA variant)
+
+// Tile configuration of the 1-CTA kernel.  BN_ = 256 (2 smem stages of 96 KB) is the throughput shape;
+// BN_ = 128 (3 stages of 64 KB) doubles the CTA count for small m, where a 256-wide grid leaves SMs idle
+// (one un-batched 640x480 frame has ~30 M tiles).  Every output element sees the same k order in both,
+// so the results are bit-identical.
+template <int BN_, int STAGES_> struct Tile {
+    static constexpr int B_TILE = BN_ * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int SMEM_BYTES = STAGES_ * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN_;       // two 128 x BN_ fp32 accumulator buffers
+    static constexpr int N_TILES = FC1_N / BN_;
+    static constexpr int COLS_PER_WARP = BN_ / 2;   // 4 lane quarters x 2 column halves = 8 epilogue warps
+    // cute::UMMA::InstrDescriptor: D = F32, A = B = F16, both K-major, M128 x N(BN_)
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,9 +106,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, M128 x N256.
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
 // Accumulation.  The tensor core adds into its fp32 TMEM accumulator with truncation (measured on
 // B200: error grows linearly with K, ~0.5 ulp per MMA step, 3e-4 relative at K = 73728).  The K loop
 // is therefore cut into chunks of `kc` k-blocks: each chunk accumulates into one of two TMEM buffers
@@ -108,11 +118,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
+template <int BN_, int STAGES_>
 __global__ void __launch_bounds__(THREADS, 1)
 fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
               const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
-              float out_scale) {
+              float out_scale, int probe_hi_only) {
+    using T = Tile<BN_, STAGES_>;
+    constexpr int STAGES = STAGES_, STAGE_BYTES = T::STAGE_BYTES, B_TILE = T::B_TILE, CW = T::COLS_PER_WARP;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -124,8 +137,8 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x & 1, m_tile = blockIdx.x >> 1;
-    const int m0 = m_tile * BM, n0 = n_tile * BN;
+    const int n_tile = blockIdx.x % T::N_TILES, m_tile = blockIdx.x / T::N_TILES;
+    const int m0 = m_tile * BM, n0 = n_tile * BN_;
     const int num_chunks = (num_kb + kc - 1) / kc;
 
     if (threadIdx.x == 0) {
@@ -134,7 +147,7 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(T::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -153,8 +166,14 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bar_full[s]);
-                mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                if (probe_hi_only) {            // bandwidth probe (wrong numerics): half the bytes, same MMAs
+                    mbar_expect_tx(full, A_TILE + B_TILE);
+                    tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
+                    tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
+                    continue;
+                }
+                mbar_expect_tx(full, STAGE_BYTES);
                 tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
                 tma_load_2d(base + A_TILE, &map_a_lo, full, kb * BK, m0);
                 tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
@@ -172,7 +191,7 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN_);
                 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {                // the small cross terms first
                     const uint32_t koff = k * UMMA_K * 2;
@@ -180,13 +199,13 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     const uint64_t a_lo = smem_desc_sw128(base + A_TILE + koff);
                     const uint64_t b_hi = smem_desc_sw128(base + 2 * A_TILE + koff);
                     const uint64_t b_lo = smem_desc_sw128(base + 2 * A_TILE + B_TILE + koff);
-                    umma_f16(acc, a_hi, b_lo, IDESC, (kin | k) != 0);
-                    umma_f16(acc, a_lo, b_hi, IDESC, 1u);
+                    umma_f16(acc, a_hi, b_lo, T::IDESC, (kin | k) != 0);
+                    umma_f16(acc, a_lo, b_hi, T::IDESC, 1u);
                 }
                 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {                // then the dominant hi*hi terms
                     const uint32_t koff = k * UMMA_K * 2;
-                    umma_f16(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), IDESC, 1u);
+                    umma_f16(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), T::IDESC, 1u);
                 }
                 umma_commit(smem_u32(&bar_empty[s]));                  // smem slot free once these MMAs retire
                 if (kin == kc - 1 || kb == num_kb - 1) umma_commit(smem_u32(&bar_tfull[buf]));   // chunk complete
@@ -195,16 +214,16 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     } else {
         // epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
         const int q = warp & 3, hcol = (warp - 2) >> 2;
-        float acc[128];
+        float acc[CW];
         #pragma unroll
-        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int j = 0; j < CW; ++j) acc[j] = 0.f;
         for (int chunk = 0; chunk < num_chunks; ++chunk) {
             const int buf = chunk & 1;
             mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(chunk >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hcol * 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + hcol * CW);
             #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CW / 32; ++c) {
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 #pragma unroll
@@ -216,10 +235,10 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         const int row = m0 + q * 32 + lane;
         if (row < m) {
-            float* orow = out + (int64_t)row * ld_out + n0 + hcol * 128;
-            const float* brow = bias + n0 + hcol * 128;
+            float* orow = out + (int64_t)row * ld_out + n0 + hcol * CW;
+            const float* brow = bias + n0 + hcol * CW;
             #pragma unroll
-            for (int j = 0; j < 128; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
                 float4 o;
                 o.x = fmaxf(fmaf(acc[j + 0], out_scale, __ldg(brow + j + 0)), 0.f);
                 o.y = fmaxf(fmaf(acc[j + 1], out_scale, __ldg(brow + j + 1)), 0.f);
@@ -232,7 +251,7 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(T::TMEM_COLS) : "memory");
     }
 }
 
@@ -285,7 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
-               float out_scale) {
+               float out_scale, int probe_hi_only) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
@@ -329,9 +348,16 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[s]), 0);
+                const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
+                if (probe_hi_only) {            // bandwidth probe (wrong numerics)
+                    if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * (A_TILE + B_HALF_TILE));
+                    else mbar_arrive_cluster(full_leader);
+                    tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
+                    tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
+                    continue;
+                }
                 if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * STAGE2_BYTES);   // both CTAs' bytes land here
                 else mbar_arrive_cluster(full_leader);
-                const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
                 tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
                 tma_load_2d_2sm(base + A_TILE, &map_a_lo, full_leader, kb * BK, m0);
                 tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
@@ -442,24 +468,50 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
     return RODC_OK;
 }
 
-// k-blocks (of 64) accumulated inside the tensor core before a drain; RODC_FC1_KC overrides (tests)
+// k-blocks (of 64) accumulated inside the tensor core before a drain; RODC_FC1_KC overrides (tests).
+// Measured on B200 against the fp64 oracle (profiles/r1h_fc1_precision.txt), max |margin error| per stage:
+//   kc = 1: 5.3e-5 / 6.8e-5 / 7.1e-5     kc = 2: 6.1e-5 / 9.4e-5 / 6.2e-5     kc = 4: 7.6e-5 / 1.25e-4 / 1.0e-4
+// kc = 2 is indistinguishable from kc = 1 (the floor is the fp32 rounding of fc2 / the register sums) and
+// halves the TMEM drains and their barrier round trips, which the pair kernel needs to run ahead.
 static int fc1_chunk_kblocks() {
     static int kc = 0;
     if (kc == 0) {
         const char* e = getenv("RODC_FC1_KC");
-        kc = e ? atoi(e) : 1;
+        kc = e ? atoi(e) : 2;
         if (kc < 1) kc = 1;
     }
     return kc;
 }
 
-// RODC_FC1_2CTA=1 selects the cta_group::2 kernel.  Measured on B200 inside the bench step it is 2-4 %
-// SLOWER than the single-CTA kernel (564 vs 579 frames/s): the step runs under sw_power_cap (SM clock
-// ~1.77 GHz), so fc1 is limited by power, not by the L2 -> SM fill rate the pair was meant to relieve.
+// Kernel choice.  fc1 alone, stage 2, m = 18944 (two waves), B200 burst timing (profiles/r1h_fc1_variants.jsonl):
+//   1 CTA  128x256 tiles, kc 1: 3.24 ms      kc 2: 3.20 ms      same, loading only the hi operands: 2.65 ms
+//   pair   256x256 tiles, kc 1: 3.42 ms      kc 2: 2.77 ms      kc 4: 2.69 ms
+// The single-CTA kernel is bound by the L2 -> SM operand stream (96 KB per k-block and SM, ~10 TB/s chip wide),
+// not by the tensor pipe; the pair kernel streams 64 KB per k-block and SM and wins once its cross-CTA drain
+// handshake happens every second k-block.  It is the default; RODC_FC1_2CTA=0 selects the single-CTA kernel.
 static bool fc1_use_2cta() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("RODC_FC1_2CTA"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("RODC_FC1_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
+}
+
+// RODC_FC1_PROBE_HI_ONLY=1: measurement aid only -- loads half the operand bytes (results are WRONG)
+static int fc1_probe_hi_only() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RODC_FC1_PROBE_HI_ONLY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
+// 128-wide N tiles when the 256-wide grid (2 CTAs per 128 rows) cannot fill the 148 SMs even once.
+// RODC_FC1_BN=128 / 256 forces one shape (tests, probes).
+static bool fc1_narrow_tiles(unsigned m_tiles) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("RODC_FC1_BN"); forced = e ? atoi(e) : 0; }
+    if (forced == 128) return true;
+    if (forced == 256) return false;
+    // one wave of 128-wide CTAs (m = 3456: 0.90 ms vs 1.29 ms for the 256-wide single-CTA grid on 54 SMs);
+    // beyond one wave the wider tiles win because they fetch A half as often
+    return m_tiles * 4u <= 148u;
 }
 
 }  // namespace tc
@@ -468,30 +520,40 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
                       float* bott, int ld_bott, cudaStream_t st) {
     using namespace tc;
     if (m <= 0) return RODC_OK;
-    RODC_CHECK_ARG(s->fc1_size == 2 * BN, "tensor fc1 is built for fc1_size == 512 (got %d)", s->fc1_size);
+    RODC_CHECK_ARG(s->fc1_size == FC1_N, "tensor fc1 is built for fc1_size == 512 (got %d)", s->fc1_size);
     RODC_CHECK_ARG(s->K % BK == 0, "K must be a multiple of %d", BK);
     RODC_CHECK_ARG(m < (1ll << 30) && ld_bott % 4 == 0, "bad m / ld_bott");
     RODC_CHECK_ARG((reinterpret_cast<uintptr_t>(bott) & 15) == 0, "bottleneck buffer must be 16-byte aligned");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    const float out_scale2 = ldexpf(1.f, -(s->a_exp + s->w_exp));
+    const unsigned m_tiles = (unsigned)((m + BM - 1) / BM);
+    const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
+    if (fc1_narrow_tiles(m_tiles)) {
+        using T = Tile<128, 3>;
+        if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
+            (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, 128)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, 128))) return rc;
+        RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+        fc1_tc_kernel<128, 3><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
+                                                                                  (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
+        RODC_LAUNCH_CHECK();
+        return RODC_OK;
+    }
     if (fc1_use_2cta()) {
         if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
             (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN_HALF)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN_HALF))) return rc;
         RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * 2u;      // (M pairs) x (2 N tiles)
         fc1_tc2_kernel<<<pairs * 2u, THREADS, SMEM2_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                 (int)(s->K / BK), fc1_chunk_kblocks(), out_scale2);
+                                                                 (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
+    using T = Tile<256, 2>;
     if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
         (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN))) return rc;
-    RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const unsigned tiles = (unsigned)((m + BM - 1) / BM) * 2u;
-    const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
-    fc1_tc_kernel<<<tiles, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                      (int)(s->K / BK), fc1_chunk_kblocks(), out_scale);
+    RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    fc1_tc_kernel<256, 2><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
+                                                                              (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

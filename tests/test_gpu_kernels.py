@@ -377,9 +377,10 @@ def test_group_rectangles_many_frames_many_tiles(nat):
     assert np.array_equal(out.cpu().numpy()[:c], _group_ref(cand, n_frames, 1))
 
 
-def test_fc1_cta_group2_variant_matches(nat):
-    """The optional cta_group::2 fc1 kernel (RODC_FC1_2CTA=1, read once per process) in a subprocess:
-    same logits as the default single-CTA kernel."""
+def test_fc1_kernel_variants_are_bit_identical(nat):
+    """The three tensor fc1 kernels (cta_group::2 pair kernel = default for large m, single-CTA 128x256 tiles,
+    single-CTA 128x128 tiles = default for small m; chosen by environment variables read once per process)
+    see the same k order per output element: bit-identical logits, also at a ragged m spanning several tiles."""
     import os
     import subprocess
     import sys
@@ -389,21 +390,25 @@ sys.path.insert(0, %r)
 from rapidobjectdetectionusingcascadedcnns_b200 import native, synth
 w = synth.xavier_stage_weights(1, 24, n_prev_bottleneck=512)
 rs = np.random.RandomState(0)
-x = torch.from_numpy(rs.randint(0, 256, (300, 24, 24, 3)).astype(np.uint8)).cuda()
+x = torch.from_numpy(rs.randint(0, 256, (1100, 24, 24, 3)).astype(np.uint8)).cuda()
 st = native.Stage(w)
-bott = torch.zeros((300, st.width), dtype=torch.float32, device="cuda")
-ws = torch.empty((st.workspace_bytes(300),), dtype=torch.uint8, device="cuda")
-logits, _ = native.stage_forward(st, native.make_source(dense=x), 0, 300, bott, ws)
+bott = torch.zeros((1100, st.width), dtype=torch.float32, device="cuda")
+ws = torch.empty((st.workspace_bytes(1100),), dtype=torch.uint8, device="cuda")
+logits, _ = native.stage_forward(st, native.make_source(dense=x), 0, 1100, bott, ws)
 np.save(sys.argv[1], logits.cpu().numpy())
 '''
     from conftest import REPO
     outs = []
-    for flag in ("0", "1"):
-        path = os.path.join("/tmp", "rodc_fc1_%s.npy" % flag)
-        env = dict(os.environ, RODC_FC1_2CTA=flag)
+    variants = [dict(RODC_FC1_BN="256", RODC_FC1_2CTA="1"), dict(RODC_FC1_BN="256", RODC_FC1_2CTA="0"),
+                dict(RODC_FC1_BN="128"), dict()]
+    for k, var in enumerate(variants):
+        path = os.path.join("/tmp", "rodc_fc1_%d.npy" % k)
+        env = {kk: vv for kk, vv in os.environ.items() if not kk.startswith("RODC_FC1")}
+        env.update(var)
         subprocess.run([sys.executable, "-c", code % REPO, path], check=True, env=env, timeout=300)
         outs.append(np.load(path))
-    assert np.array_equal(outs[0], outs[1])          # same MMA order -> bit-identical
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)            # same MMA order per element -> bit-identical
 
 
 @pytest.mark.parametrize("spec", [
