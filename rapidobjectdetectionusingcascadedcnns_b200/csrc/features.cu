@@ -361,15 +361,16 @@ template <int S> struct StreamCfg { static constexpr int NQ = S >= 48 ? 4 : (S >
 
 template <int OUT_SPLIT, int S>
 __global__ void __launch_bounds__(FEAT_THREADS, 2)
-features_stream_kernel(SrcDev src, int64_t first, int64_t n,
+features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
     constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NP = 2 * TR;    // NP pixels per thread and row
     constexpr int NQ = StreamCfg<S>::NQ, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
+    constexpr int WIN_BYTES = S * S * 3, UPW = S * S / 4, UPI = WPC * UPW;   // 12-byte units (4 pixels) per window / iteration
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* inh0 = reinterpret_cast<__half*>(smem_raw);                  // [2 buffers][WPC windows][INH]
-    int* tabs0 = reinterpret_cast<int*>(smem_raw + (size_t)2 * WPC * INH * 2);   // [WPC][6 S]
+    uint8_t* raw0 = smem_raw + (size_t)2 * WPC * INH * 2;                // [2 buffers][WPC windows][WIN_BYTES] u8 as fetched
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -391,52 +392,59 @@ features_stream_kernel(SrcDev src, int64_t first, int64_t n,
             }
     const __half one_h = __float2half_rn(pix_scale);
 
+    // Input staging.  The u8 windows of iteration i+1 are fetched with cp.async into a raw buffer while
+    // iteration i computes (a window is 6.9 KB of the 295 KB it produces, but its load latency was 1/3 of the
+    // kernel when it sat between two barriers); every thread converts exactly the bytes it fetched itself, so the
+    // only barrier per iteration is the one that publishes the fp16 image.  The zero border (SAME padding) of
+    // both fp16 buffers is written once: interior stores never touch it.
+    {
+        uint4* z = reinterpret_cast<uint4*>(inh0);
+        for (int i = tid; i < 2 * WPC * INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    auto prefetch = [&](int64_t wrel0, int buf) {
+        for (int u = tid; u < UPI; u += FEAT_THREADS) {
+            const int sl = u / UPW, q = u - sl * UPW;
+            if (wrel0 + sl < n) {
+                const uint8_t* src = dense + (first + wrel0 + sl) * (int64_t)WIN_BYTES + q * 12;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw0 + ((size_t)buf * WPC + sl) * WIN_BYTES + q * 12);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4), "l"(src + 4) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 8), "l"(src + 8) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch((int64_t)blockIdx.x * WPC, 0);
+    __syncthreads();                                           // zero fill visible before the first interior stores
+
     int iter = 0;
     for (int64_t wrel0 = (int64_t)blockIdx.x * WPC; wrel0 < n; wrel0 += (int64_t)gridDim.x * WPC, ++iter) {
         __half* inhb = inh0 + (size_t)(iter & 1) * WPC * INH;
-        // ---- stage WPC windows as fp16 [P][P][4] = (r, g, b, 1) * 2^p, zero border
-        {
-            uint4* z = reinterpret_cast<uint4*>(inhb);
-            for (int i = tid; i < WPC * INH / 8; i += FEAT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (src.kind == RODC_SRC_RECROP) {
-            for (int sl = 0; sl < WPC; ++sl)
-                if (wrel0 + sl < n) {
-                    const Crop c = make_crop(src, first + wrel0 + sl);
-                    fill_recrop_tables(c, S, tabs0 + sl * 6 * S);      // safe: everyone left the previous staging
-                }
-        }
-        __syncthreads();                                       // zero fill (and tables) visible
-        for (int i = tid; i < WPC * S * S; i += FEAT_THREADS) {
-            const int sl = i / (S * S), r = i - sl * S * S;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's bytes of the current windows have landed
+        const int64_t next0 = wrel0 + (int64_t)gridDim.x * WPC;
+        if (next0 < n) prefetch(next0, (iter + 1) & 1);
+        // ---- fp16 [P][P][4] = (r, g, b, 1) * 2^p from the thread's own 4-pixel units
+        for (int u = tid; u < UPI; u += FEAT_THREADS) {
+            const int sl = u / UPW, q = u - sl * UPW;
             if (wrel0 + sl >= n) continue;
-            const int64_t w = first + wrel0 + sl;
-            const int y = r / S, x = r - y * S;
-            float p0, p1, p2;
-            if (src.kind == RODC_SRC_RECROP) {
-                const Crop c = make_crop(src, w);
-                int px[3];
-                recrop_pixel(c, S, tabs0 + sl * 6 * S, y, x, px);
-                p0 = (float)px[0]; p1 = (float)px[1]; p2 = (float)px[2];
-            } else {
-                const uint8_t* p; int pitch;
-                if (src.kind == RODC_SRC_DENSE) { p = src.dense + w * (int64_t)S * S * 3; pitch = S * 3; }
-                else if (src.kind == RODC_SRC_GATHER) { p = src.gather_base + src.win_off[w]; pitch = src.win_pitch[w]; }
-                else {
-                    const int64_t f = w / src.n_windows, j = w - f * src.n_windows;
-                    const int32_t* wr = src.win + j * 8;
-                    const LevelInfo& lv = src.levels[wr[0]];
-                    p = src.pyramid + f * src.pyramid_bytes + lv.byte_off + ((int64_t)wr[2] * lv.w + wr[1]) * 3;
-                    pitch = lv.w * 3;
-                }
-                const uint8_t* q = p + (int64_t)y * pitch + x * 3;
-                p0 = (float)q[0]; p1 = (float)q[1]; p2 = (float)q[2];
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw0 + ((size_t)(iter & 1) * WPC + sl) * WIN_BYTES + q * 12);
+            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+            const int p0 = 4 * q, y = p0 / S, x = p0 - y * S;
+            uint2* d = reinterpret_cast<uint2*>(inhb + (size_t)sl * INH + ((y + 1) * P + (x + 1)) * 4);
+            const uint32_t px[4][3] = {{w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u},
+                                       {w0 >> 24, w1 & 255u, (w1 >> 8) & 255u},
+                                       {(w1 >> 16) & 255u, w1 >> 24, w2 & 255u},
+                                       {(w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24}};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2 rg = __floats2half2_rn((float)px[i][0] * pix_scale, (float)px[i][1] * pix_scale);
+                const __half2 b1 = __halves2half2(__float2half_rn((float)px[i][2] * pix_scale), one_h);
+                uint2 o;
+                o.x = *reinterpret_cast<const uint32_t*>(&rg); o.y = *reinterpret_cast<const uint32_t*>(&b1);
+                d[i] = o;
             }
-            __half2* d = reinterpret_cast<__half2*>(inhb + (size_t)sl * INH + ((y + 1) * P + (x + 1)) * 4);
-            d[0] = __floats2half2_rn(p0 * pix_scale, p1 * pix_scale);
-            d[1] = __halves2half2(__float2half_rn(p2 * pix_scale), one_h);
         }
-        __syncthreads();                                       // windows staged
+        __syncthreads();                                       // windows staged (and everyone left iteration iter - 1)
 
         const int64_t wrel = wrel0 + slot;
         if (wrel >= n) continue;                               // tail: this warp's window slot is empty
@@ -549,7 +557,7 @@ template <int S>
 static size_t feat3_smem_bytes() {
     constexpr int P = S + 2;
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;
-    return (size_t)2 * StreamCfg<S>::WPC * INH * 2 + (size_t)StreamCfg<S>::WPC * 6 * S * 4;
+    return (size_t)2 * StreamCfg<S>::WPC * INH * 2 + (size_t)2 * StreamCfg<S>::WPC * S * S * 3;
 }
 
 static size_t feat2_smem_bytes(int S, int R) {
@@ -709,6 +717,14 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     return RODC_OK;
 }
 
+int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st) {
+    if (n <= 0) return RODC_OK;
+    const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
+    source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out);
+    RODC_LAUNCH_CHECK();
+    return RODC_OK;
+}
+
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
                     float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch) {
     if (n <= 0) return RODC_OK;
@@ -739,12 +755,14 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
     // RODC_FEATURES_GENERIC=1 forces the generic kernel (cross-check of the specialised one)
     static int use_v2 = -1;
     if (use_v2 < 0) { const char* e = getenv("RODC_FEATURES_GENERIC"); use_v2 = (e && e[0] == '1') ? 1 : 0; }
-    if (!use_v2 && (S == 12 || S == 24 || S == 48)) {
+    // the streaming kernels read materialised u8 windows (rodc_stage_forward copies every other source into its
+    // workspace first); other sources and sizes take the generic kernel
+    if (!use_v2 && (S == 12 || S == 24 || S == 48) && src.kind == RODC_SRC_DENSE && (reinterpret_cast<uintptr_t>(src.dense) & 3) == 0) {
 #define RODC_LAUNCH_FEAT3(SPLIT, ST_)                                                                                      \
         do {                                                                                                              \
             const size_t smem = feat3_smem_bytes<ST_>();                                                                  \
             RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->conv_frag_perm,           \
+            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,     \
                                                                                  ldexpf(1.f, s->a_exp - s->c_exp),          \
                                                                                  ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo); \
         } while (0)
@@ -790,8 +808,5 @@ extern "C" int rodc_source_windows(const rodc_window_source* src, int64_t first,
     if (n <= 0) return RODC_OK;
     SrcDev d;
     int rc = resolve_source(src, size, &d); if (rc) return rc;
-    const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
-    source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), as_stream(stream)>>>(d, first, n, size, out);
-    RODC_LAUNCH_CHECK();
-    return RODC_OK;
+    return launch_source_windows(d, first, n, size, out, as_stream(stream));
 }

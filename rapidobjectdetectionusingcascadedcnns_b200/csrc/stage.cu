@@ -283,11 +283,15 @@ static int64_t general_scratch_bytes(const rodc_stage* s) {
     return s->general ? (int64_t)GENERAL_CTAS * 2 * s->max_act * 4 + 256 : 0;
 }
 
-// workspace = feature chunk: fp32 [m,K] (SIMT) or two fp16 planes [m,K] (tensor): 4*K bytes per window
+// bytes of one materialised u8 window (non-dense sources are copied into the workspace before the feature kernel)
+static int64_t window_bytes(const rodc_stage* s) { return ((int64_t)s->in_size * s->in_size * 3 + 15) / 16 * 16; }
+
+// workspace = feature chunk: fp32 [m,K] (SIMT) or two fp16 planes [m,K] (tensor): 4*K bytes per window,
+// followed by the chunk's u8 windows [m, S, S, 3]
 static int64_t chunk_windows(const rodc_stage* s, int64_t workspace_bytes) {
     workspace_bytes -= general_scratch_bytes(s);
     if (workspace_bytes < 0) return 0;
-    int64_t m = workspace_bytes / (s->K * 4);
+    int64_t m = workspace_bytes / (s->K * 4 + window_bytes(s));
     if (m >= 128) m = m / 128 * 128;
     return m;
 }
@@ -300,7 +304,7 @@ extern "C" int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, in
     const int64_t cap = 148 * 128 * (s->K > 40000 ? 1 : (s->K > 10000 ? 2 : 8));
     if (m > cap) m = cap;
     if (m < 128) m = 128;
-    return m * s->K * 4 + general_scratch_bytes(s);
+    return m * (s->K * 4 + window_bytes(s)) + general_scratch_bytes(s);
 }
 
 extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
@@ -323,19 +327,32 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         // the tensor fc1 needs fc1_size == 512 and K % 64 == 0; anything else runs the fp32 SIMT GEMM
         if (impl == RODC_IMPL_TENSOR && (s->fc1_size != 512 || s->K % 64 != 0)) impl = RODC_IMPL_SIMT;
     }
+    // The default-architecture feature kernels stream dense u8 windows (asynchronous prefetch); pyramid / re-crop /
+    // gather sources are materialised per chunk first -- a window is 2 % of the bytes it expands to, and a
+    // separate, fully occupied kernel hides the gather latency that stalled the fused producer.
+    const bool materialise = !s->general && sd.kind != RODC_SRC_DENSE;
+    uint8_t* dense_ws = reinterpret_cast<uint8_t*>(workspace) + chunk * s->K * 4;
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t m = (n - c0) < chunk ? (n - c0) : chunk;
         float* bott = bottleneck + c0 * ld_bott;
+        SrcDev csrc = sd;
+        int64_t cfirst = first + c0;
+        if (materialise) {
+            if ((rc = launch_source_windows(sd, first + c0, m, s->in_size, dense_ws, st))) return rc;
+            memset(&csrc, 0, sizeof(csrc));
+            csrc.kind = RODC_SRC_DENSE; csrc.dense = dense_ws;
+            cfirst = 0;
+        }
         if (impl == RODC_IMPL_SIMT) {
             float* feat = reinterpret_cast<float*>(workspace);
-            if ((rc = launch_features(s, sd, first + c0, m, feat, nullptr, nullptr, st, gscratch))) return rc;
+            if ((rc = launch_features(s, csrc, cfirst, m, feat, nullptr, nullptr, st, gscratch))) return rc;
             profile_begin(st);
             if ((rc = launch_fc1_simt(s, feat, m, bott, ld_bott, st))) return rc;
             profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         } else {
             __half* hi = reinterpret_cast<__half*>(workspace);
             __half* lo = hi + m * s->K;
-            if ((rc = launch_features(s, sd, first + c0, m, nullptr, hi, lo, st, gscratch))) return rc;
+            if ((rc = launch_features(s, csrc, cfirst, m, nullptr, hi, lo, st, gscratch))) return rc;
             profile_begin(st);
             if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
             profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);

@@ -50,6 +50,7 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out);
 // features.cu
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
                     float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch = nullptr);
+int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st);
 constexpr int GENERAL_CTAS = 296;     // persistent CTAs of the general-architecture feature kernel
 // fc.cu
 int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bott, int ld_bott, cudaStream_t st);

@@ -170,11 +170,14 @@ class CascadeEngine:
     def _impl() -> int:
         return native.IMPL_SIMT if cf.get("fc1_impl") == cf.FC1_IMPL_SIMT else native.IMPL_TENSOR
 
-    def _count_stage_launches(self, stage: native.Stage, n: int, ws_bytes: int):
-        chunk = max(1, ws_bytes // (stage.K * 4))
+    def _count_stage_launches(self, stage: native.Stage, n: int, ws_bytes: int, dense: bool):
+        """Launches of one ``rodc_stage_forward``: per chunk (window copy unless the source is dense) + features +
+        fc1, then one fc2/softmax."""
+        win = (stage.in_size * stage.in_size * 3 + 15) // 16 * 16
+        chunk = max(1, ws_bytes // (stage.K * 4 + win))
         if chunk >= 128:
             chunk = chunk // 128 * 128
-        self.kernel_launches += 2 * ((n + chunk - 1) // chunk) + 1
+        self.kernel_launches += (2 if dense else 3) * ((n + chunk - 1) // chunk) + 1
 
     # ------------------------------------------------------------------ stages on a window set
     def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
@@ -206,7 +209,7 @@ class CascadeEngine:
             if keep_trace:                      # the stage's u8 input, i.e. the reference's windows_raw (tests)
                 trace["X"].append(native.source_windows(src, 0, n, st.in_size, dev))
             logits, probs = native.stage_forward(st, src, 0, n, bott, ws[:ws_bytes], impl)
-            self._count_stage_launches(st, n, ws_bytes)
+            self._count_stage_launches(st, n, ws_bytes, dense=src.kind == native.SRC_DENSE)
             # single net: keep argmax != background <=> p[1] > p[0] <=> p[1] > 0.5 (ties -> background,
             # np.argmax picks index 0), confidence = p[argmax] = p[1]   (inference_app.py:140-149)
             thr = 0.5 if self.single else self._threshold(i)
