@@ -94,22 +94,6 @@ __device__ __forceinline__ void fill_recrop_tables(const Crop& c, int S, int* ta
     }
 }
 
-// Standalone K4 (API / parity): out [n,S,S,3] u8.  grid = n windows, block 128.
-__global__ void __launch_bounds__(128) recrop_kernel(SrcDev src, int64_t n, int S, uint8_t* __restrict__ out) {
-    extern __shared__ int tabs[];
-    const int64_t w = blockIdx.x;
-    if (w >= n) return;
-    const Crop c = make_crop(src, w);
-    fill_recrop_tables(c, S, tabs);
-    __syncthreads();
-    uint8_t* o = out + w * (int64_t)S * S * 3;
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
-        int px[3];
-        recrop_pixel(c, S, tabs, i / S, i % S, px);
-        o[i * 3 + 0] = (uint8_t)px[0]; o[i * 3 + 1] = (uint8_t)px[1]; o[i * 3 + 2] = (uint8_t)px[2];
-    }
-}
-
 // The u8 input of a stage for ANY window source (what the reference holds as windows_raw and feeds to X,
 // app/inference_cascade_app.py:200-202): out [n,S,S,3].  API / parity path; the stage kernels read the
 // sources in place.
@@ -144,6 +128,108 @@ __global__ void __launch_bounds__(128) source_windows_kernel(SrcDev src, int64_t
         for (int i = threadIdx.x; i < S * S * 3; i += blockDim.x) {
             const int y = i / (S * 3), b = i - y * S * 3;
             o[i] = p[(int64_t)y * pitch + b];
+        }
+    }
+}
+
+// K4 for the default cascade sizes: cv2.resize(window.raw_norm, (S, S)) of every survivor into dense u8 windows
+// (app/inference_cascade_app.py:363-373).  A thread owns 4 adjacent output pixels of a row (its x taps live in
+// registers, 12 output bytes leave as three 32-bit stores) and walks down the rows; the tap tables of a window are
+// built once by the first 2 S threads.  Same arithmetic as recrop_pixel, without the per-pixel divisions and table
+// reads that made the generic kernel issue bound (147 -> ~60 instructions per pixel).
+// Bytes p[0 .. len) (len = 3 or 6) as lo = bytes 0..3, hi = bytes 4..5, fetched with one or two aligned 8-byte
+// loads instead of `len` byte loads (the scattered byte loads saturated the L1 request path).  The aligned word
+// that holds a valid byte never leaves that byte's 256-byte allocation granule, so nothing outside the frames
+// buffer is touched.
+__device__ __forceinline__ void load_taps(const uint8_t* p, int len, uint32_t& lo, uint32_t& hi) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    const int off = (int)(a & 7);
+    const unsigned long long w0 = __ldg(q);
+    const unsigned long long w1 = off + len > 8 ? __ldg(q + 1) : 0ull;
+    const int sh = off * 8;
+    const unsigned long long v = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
+}
+
+template <int S, int RPP>
+__global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev src, int64_t first, int64_t n,
+                                                                       uint8_t* __restrict__ out) {
+    constexpr int UN = S / 4, THREADS = UN * RPP;
+    __shared__ int tabs[6 * S];
+    const int u = threadIdx.x % UN, r0 = threadIdx.x / UN;
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
+        const Crop c = make_crop(src, first + wrel);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + wrel * (int64_t)S * S * 3);
+        const bool empty = c.sw <= 0 || c.sh <= 0;
+        const bool same = c.sw == S && c.sh == S, half = c.sw == 2 * S && c.sh == 2 * S;
+        if (empty || same || half) {                            // uniform per window: zero / copy / INTER_AREA 2x2
+            for (int r = r0; r < S; r += RPP) {
+                uint32_t w[3] = {0u, 0u, 0u};
+                if (!empty) {
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int x = 4 * u + i;
+                        #pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            uint32_t v;
+                            if (same) v = c.base[(int64_t)r * c.pitch + x * 3 + ch];
+                            else {
+                                const uint8_t* p = c.base + (int64_t)(2 * r) * c.pitch + (2 * x) * 3 + ch;
+                                v = ((uint32_t)p[0] + p[3] + p[c.pitch] + p[c.pitch + 3] + 2u) >> 2;
+                            }
+                            const int b = i * 3 + ch;
+                            w[b >> 2] |= v << (8 * (b & 3));
+                        }
+                    }
+                }
+                uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
+                d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
+            }
+            continue;
+        }
+        __syncthreads();                                        // the previous window's tables are free
+        for (int t = threadIdx.x; t < 2 * S; t += THREADS) {
+            int sidx, a0, a1;
+            if (t < S) { cv_tap(t, c.sw, S, true, sidx, a0, a1); tabs[t] = sidx; tabs[S + t] = a0; tabs[2 * S + t] = a1; }
+            else { const int d = t - S; cv_tap(d, c.sh, S, false, sidx, a0, a1); tabs[3 * S + d] = sidx; tabs[4 * S + d] = a0; tabs[5 * S + d] = a1; }
+        }
+        __syncthreads();
+        int xo[4], xlen[4], xa0[4], xa1[4];                     // byte offset of the first x tap, bytes to fetch, weights
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = 4 * u + i, sx = tabs[x];
+            xo[i] = sx * 3;
+            xlen[i] = sx + 1 <= c.sw - 1 ? 6 : 3;               // right border: the second tap is the same pixel (weight 0)
+            xa0[i] = tabs[S + x]; xa1[i] = tabs[2 * S + x];
+        }
+        for (int r = r0; r < S; r += RPP) {
+            const int sy = tabs[3 * S + r], b0 = tabs[4 * S + r], b1 = tabs[5 * S + r];
+            const int y0 = min(max(sy, 0), c.sh - 1), y1 = min(max(sy + 1, 0), c.sh - 1);
+            const uint8_t* p0 = c.base + (int64_t)y0 * c.pitch;
+            const uint8_t* p1 = c.base + (int64_t)y1 * c.pitch;
+            uint32_t w[3] = {0u, 0u, 0u};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t l0, h0, l1, h1;                        // the two taps of both rows: 6 adjacent bytes each
+                load_taps(p0 + xo[i], xlen[i], l0, h0);
+                load_taps(p1 + xo[i], xlen[i], l1, h1);
+                // xlen == 3: the bytes of the "second tap" are undefined, but its weight xa1 is 0 (cv_tap clamps f to 0)
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int t00 = (int)((l0 >> (8 * ch)) & 255u), t10 = (int)((l1 >> (8 * ch)) & 255u);
+                    const int t01 = ch == 0 ? (int)(l0 >> 24) : (int)((h0 >> (8 * (ch - 1))) & 255u);
+                    const int t11 = ch == 0 ? (int)(l1 >> 24) : (int)((h1 >> (8 * (ch - 1))) & 255u);
+                    const int T0 = t00 * xa0[i] + t01 * xa1[i];
+                    const int T1 = t10 * xa0[i] + t11 * xa1[i];
+                    // weights are >= 0 and sum to 2048 per axis, so the result is already inside 0..255
+                    const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 255u;
+                    const int b = i * 3 + ch;
+                    w[b >> 2] |= v << (8 * (b & 3));
+                }
+            }
+            uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
+            d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
         }
     }
 }
@@ -456,6 +542,7 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C + tofs : nullptr;
         __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C + tofs : nullptr;
         const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + (lane_in ? xbase : 0) * 4) + t;
+        const bool has_left = g > 0, has_right = g < 7;
 
         // sliding window of horizontal maxima of (conv + bias) * 2^a_exp, BEFORE the ReLU: the ReLU commutes
         // with the max and is applied once at the output as max(., 0); zeros stand for SAME padding.
@@ -499,10 +586,10 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                 // horizontal 3-max: only the first / last pixel of a thread need a neighbour lane
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float ln = __shfl_sync(0xffffffffu, v[NP - 1][c], (lane + 28) & 31);   // last pixel of lane group g-1
-                    float rn = __shfl_sync(0xffffffffu, v[0][c], (lane + 4) & 31);         // first pixel of lane group g+1
-                    ln = g > 0 ? ln : 0.f;
-                    rn = g < 7 ? rn : 0.f;
+                    float ln = __shfl_up_sync(0xffffffffu, v[NP - 1][c], 4);               // last pixel of lane group g-1
+                    float rn = __shfl_down_sync(0xffffffffu, v[0][c], 4);                  // first pixel of lane group g+1
+                    ln = has_left ? ln : 0.f;
+                    rn = has_right ? rn : 0.f;
                     #pragma unroll
                     for (int i = 0; i < NP; ++i) {
                         const float l = i > 0 ? v[i > 0 ? i - 1 : 0][c] : ln;
@@ -720,7 +807,10 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
 int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st) {
     if (n <= 0) return RODC_OK;
     const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
-    source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out);
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    if (aligned && src.kind == RODC_SRC_RECROP && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out);
+    else if (aligned && src.kind == RODC_SRC_RECROP && size == 24) recrop_windows_kernel<24, 24><<<grid, 144, 0, st>>>(src, first, n, out);
+    else source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
@@ -796,9 +886,7 @@ extern "C" int rodc_recrop(const uint8_t* frames_base, const int64_t* frame_off,
     if (n <= 0) return RODC_OK;
     SrcDev d; memset(&d, 0, sizeof(d));
     d.kind = RODC_SRC_RECROP; d.frames_base = frames_base; d.frame_off = frame_off; d.frame_hw = frame_hw; d.meta = meta;
-    recrop_kernel<<<(unsigned)n, 128, (size_t)6 * size * sizeof(int), as_stream(stream)>>>(d, n, size, out);
-    RODC_LAUNCH_CHECK();
-    return RODC_OK;
+    return launch_source_windows(d, 0, n, size, out, as_stream(stream));
 }
 
 extern "C" int rodc_source_windows(const rodc_window_source* src, int64_t first, int64_t n, int size, uint8_t* out,
