@@ -36,7 +36,8 @@ UNIT = "frames/s"
 FRAME_H, FRAME_W = 480, 640
 WINDOWS_PER_FRAME = 5061
 FLOPS_PER_WINDOW = [4969472, 19873792, 79484928]       # SURVEY.md §8a (2*MAC), stages 0/1/2
-NCU_FC1_TRAFFIC_BYTES = 5890980000 + 26478336          # dram__bytes_read.sum + dram__bytes_write.sum, m = 18944 launch
+NCU_FC1_TRAFFIC_BYTES = 5925631000 + 26252288          # dram__bytes_read.sum + dram__bytes_write.sum of one m = 18944 launch
+                                                       # of the pair kernel (profiles/r1h_ncu_full_fc1_pair.txt)
 
 
 def measured_peaks():
@@ -293,7 +294,7 @@ def main():
             "roofline": {"kernel": "rodc::tc::fc1_tc2_kernel (cta_group::2 pairs)" if args.fc1 == "tensor" else "rodc::fc1_simt_kernel",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
-                         # ncu --set full, same launch shape (profiles/r1b_ncu_full_fc1.txt): dram read + write
+                         # ncu --set full, same launch shape (profiles/r1h_ncu_full_fc1_pair.txt): dram read + write
                          "traffic": NCU_FC1_TRAFFIC_BYTES if abs(dom_windows - 18944) < 1 else None,
                          "algorithmic_bytes": dom_windows * 73728 * 4 + 512 * 73728 * 4 + dom_windows * 512 * 4,
                          "peak_source": "%s bf16_tflops_sustained / 3 (each product = 3 fp16 MMAs); the denominator is cuBLAS "

@@ -1,16 +1,18 @@
-// K2a (+ fused K4): per-window conv3x3(3->C)+bias+ReLU -> maxpool3x3/1 SAME -> NHWC flatten.
+// K2a + K4: per-window conv3x3(3->C)+bias+ReLU -> maxpool3x3/1 SAME -> NHWC flatten.
 //
 // Graph: network/net.py:172-240 (conv_layer_0, pool_layer_0), network/net_builder.py:6-60.
 // SAME padding is per window: zeros for the conv; the pool ignores padding, which for
 // post-ReLU (>= 0) data equals zero padding.  Raw 0..255 pixels are fed without any
 // normalisation (app/inference_cascade_app.py:200-202).
 //
-// Window sources (the u8 window never round-trips through HBM on the fast path):
-//   PYRAMID  stage 0 reads its 12x12 window in place from the packed pyramid (K1 output)
-//   RECROP   stages >= 1 crop the survivor's *_norm box from the ORIGINAL frame and apply
-//            cv2.resize INTER_LINEAR (8U fixed point, 2x INTER_AREA shortcut) on the fly
-//            (app/inference_cascade_app.py:363-373) -- this is K4 fused as the producer
-//   DENSE    caller-materialised windows (run_inference_on_windows / run_inference_on_raw_data)
+// Window sources.  rodc_stage_forward materialises every non-dense source per chunk (source_windows_kernel /
+// recrop_windows_kernel) and the streaming feature kernels read dense u8 windows; the generic feature kernels
+// still read every source in place:
+//   PYRAMID  stage-0 windows inside the packed pyramid (K1 output)
+//   GATHER   per-window (byte offset, row pitch) into any buffer (mixed frame shapes, resize-then-crop branch)
+//   RECROP   stages >= 1: the survivor's *_norm box of the ORIGINAL frame through cv2.resize INTER_LINEAR
+//            (8U fixed point, 2x INTER_AREA shortcut), app/inference_cascade_app.py:363-373 (K4)
+//   DENSE    materialised windows (run_inference_on_windows / run_inference_on_raw_data / the workspace copy)
 //
 // Output: fp32 features (SIMT fc1 / tests) or the split-fp16 A operand of the tensor fc1:
 //   f * 2^a_exp = hi + lo  (hi, lo fp16; 22 significant bits), planes [n, K] K-contiguous.
