@@ -456,6 +456,8 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
     constexpr int NQ = StreamCfg<S>::NQ, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
     constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
     constexpr int WIN_BYTES = S * S * 3, UPW = S * S / 4, UPI = WPC * UPW;   // 12-byte units (4 pixels) per window / iteration
+    constexpr bool ALL_IN = 8 * NP == S;                                 // every lane group owns pixels of the row
+    static_assert(S % NP == 0, "a lane group must be completely inside or outside the row");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* inh0 = reinterpret_cast<__half*>(smem_raw);                  // [2 buffers][WPC windows][INH]
     uint8_t* raw0 = smem_raw + (size_t)2 * WPC * INH * 2;                // [2 buffers][WPC windows][WIN_BYTES] u8 as fetched
@@ -463,7 +465,7 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int cg = warp & 1, part = (warp >> 1) % NQ, slot = (warp >> 1) / NQ;
-    const int ya = part * RQ, yb = ya + RQ;
+    const int ya = part * RQ;
     const int xbase = NP * g;                                             // this thread's pixels: xbase .. xbase + NP - 1
     const bool lane_in = xbase < S;                                      // S = 24 / 12 leave lane groups 6, 7 idle
 
@@ -539,12 +541,18 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         const __half* inh = inhb + (size_t)slot * INH;
 
         // thread-constant output pointers (row offset added per row, pixel offsets are immediates)
-        const int64_t tofs = (int64_t)xbase * C + 16 * cg + 4 * t;
-        float* of = OUT_SPLIT ? nullptr : out_f32 + wrel * (int64_t)S * S * C + tofs;
-        __half* oh = OUT_SPLIT ? out_hi + wrel * (int64_t)S * S * C + tofs : nullptr;
-        __half* ol = OUT_SPLIT ? out_lo + wrel * (int64_t)S * S * C + tofs : nullptr;
+        // ONE running output pointer per thread (element offset of output row ya - 2 + rr; the lo plane sits at
+        // the kernel-uniform distance out_lo - out_hi), opaque so that it is carried instead of being rebuilt from %tid
+        int64_t oofs = wrel * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
+        asm volatile("" : "+l"(oofs));
+        const int64_t lo_delta = OUT_SPLIT ? out_lo - out_hi : 0;
         const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + (lane_in ? xbase : 0) * 4) + t;
-        const bool has_left = g > 0, has_right = g < 7;
+        // lane / warp role flags in ONE register the compiler cannot rematerialise from %tid (S2R is a long-latency
+        // read and was re-issued in every row): bit 0 left neighbour group, 1 right neighbour group, 2 first row
+        // part, 3 last row part, 4 lane owns pixels
+        int flags = (g > 0 ? 1 : 0) | (g < 7 ? 2 : 0) | (part == 0 ? 4 : 0) | (part == NQ - 1 ? 8 : 0) | (lane_in ? 16 : 0);
+        asm volatile("" : "+r"(flags));
+        const bool has_left = flags & 1, has_right = flags & 2;
 
         // sliding window of horizontal maxima of (conv + bias) * 2^a_exp, BEFORE the ReLU: the ReLU commutes
         // with the max and is applied once at the output as max(., 0); zeros stand for SAME padding.
@@ -554,15 +562,19 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
             #pragma unroll
             for (int c = 0; c < 4; ++c) { hA[i][c] = 0.f; hB[i][c] = 0.f; }
 
+        // Row loop in part-relative terms (rr = 0 .. RQ + 1 <-> image row ya - 1 + rr) with running pointers, so
+        // that nothing derived from %tid is needed inside it (the compiler re-read %tid every row otherwise).
+        const bool first_part = flags & 4, last_part = flags & 8, owns = flags & 16;
+        const uint32_t* arow = abase + (ya - 1) * P * 2;      // row ya - 1 (never dereferenced when that is row -1)
         #pragma unroll 1
-        for (int yy = ya - 1; yy <= yb; ++yy) {
+        for (int rr = 0; rr <= RQ + 1; ++rr, arow += P * 2, oofs += S * C) {
             float hc[NP][4];
-            if (yy >= 0 && yy < S) {
+            if (!((rr == 0 && first_part) || (rr == RQ + 1 && last_part))) {
                 float v[NP][4];
                 #pragma unroll
                 for (int j = 0; j < TR; ++j) {
                     // fragment row g -> pixel xbase + 2 j, row g + 8 -> pixel xbase + 2 j + 1
-                    const uint32_t* base = abase + (yy * P + 2 * j) * 2;
+                    const uint32_t* base = arow + 2 * j * 2;
                     float acc[2][4];
                     #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) { acc[sub][0] = acc[sub][1] = acc[sub][2] = acc[sub][3] = 0.f; }
@@ -576,13 +588,15 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                             mma16816(acc[sub], a0, a1, a2, a3, bf[ky][sub][0][0], bf[ky][sub][0][1]);
                         }
                     }
-                    const bool in0 = xbase + 2 * j < S, in1 = xbase + 2 * j + 1 < S;
+                    // S is a multiple of NP, so a lane group is either completely inside the row or idle (zeros
+                    // stand for the SAME padding); at S = 48 all eight groups are inside
+                    const bool in = ALL_IN || owns;
                     #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
-                        v[2 * j][2 * sub + 0] = in0 ? acc[sub][0] : 0.f;
-                        v[2 * j][2 * sub + 1] = in0 ? acc[sub][1] : 0.f;
-                        v[2 * j + 1][2 * sub + 0] = in1 ? acc[sub][2] : 0.f;
-                        v[2 * j + 1][2 * sub + 1] = in1 ? acc[sub][3] : 0.f;
+                        v[2 * j][2 * sub + 0] = in ? acc[sub][0] : 0.f;
+                        v[2 * j][2 * sub + 1] = in ? acc[sub][1] : 0.f;
+                        v[2 * j + 1][2 * sub + 0] = in ? acc[sub][2] : 0.f;
+                        v[2 * j + 1][2 * sub + 1] = in ? acc[sub][3] : 0.f;
                     }
                 }
                 // horizontal 3-max: only the first / last pixel of a thread need a neighbour lane
@@ -606,12 +620,10 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                     for (int c = 0; c < 4; ++c) hc[i][c] = 0.f;
             }
             // vertical: pooled row yy-1 = relu(max(h[yy-2], h[yy-1], h[yy]))
-            const int yo = yy - 1;
-            if (yo >= ya && yo < yb && lane_in) {
-                const int64_t rofs = (int64_t)yo * S * C;
+            if (rr >= 2 && owns) {                             // output row ya - 2 + rr, rr = 2 .. RQ + 1
                 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
-                    if (xbase + i < S) {
+                    {
                         float m[4];
                         #pragma unroll
                         for (int c = 0; c < 4; ++c) m[c] = fmaxf(fmaxf(hA[i][c], hc[i][c]), 0.f);
@@ -622,10 +634,10 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                             uint2 uh, ul;
                             uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
                             ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-                            *reinterpret_cast<uint2*>(oh + rofs + i * C) = uh;
-                            *reinterpret_cast<uint2*>(ol + rofs + i * C) = ul;
+                            *reinterpret_cast<uint2*>(out_hi + oofs + i * C) = uh;
+                            *reinterpret_cast<uint2*>(out_hi + oofs + lo_delta + i * C) = ul;
                         } else {
-                            *reinterpret_cast<float4*>(of + rofs + i * C) =
+                            *reinterpret_cast<float4*>(out_f32 + oofs + i * C) =
                                 make_float4(m[0] * inv_a_scale, m[1] * inv_a_scale, m[2] * inv_a_scale, m[3] * inv_a_scale);
                         }
                     }
