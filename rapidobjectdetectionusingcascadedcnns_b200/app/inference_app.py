@@ -136,7 +136,7 @@ class InferenceApp(AbstractInferenceApp):
         self._init_tf()
         self._update_input_dims()
         if len({f.shape for f in frames}) == 1:
-            res = self._engine.run_frames(self._engine.stage_host_frames(frames))
+            res = self._engine.run_frames(self._engine.upload_host_frames(frames))
             self._log_stage_stats(res)
             return self._boxes_from_result(res, infos, len(infos))
         # several shapes: one merged set of stage launches (internal frame ids are grouped by shape)

@@ -304,6 +304,40 @@ class CascadeEngine:
                 dst[i] = f
         return view
 
+    def upload_host_frames(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+        """Same-size host frames -> ``[n,H,W,3]`` u8 on the device.  The frames are gathered into the pinned
+        buffer group by group and every group's H2D copy is issued as soon as it is staged, so the DMA of group g
+        runs while the host gathers group g + 1 (the reference re-reads the files per scale,
+        `data/image_info.py:228-240`; here a frame crosses PCIe once)."""
+        n = len(frames)
+        h, w, _ = frames[0].shape
+        need = n * h * w * 3
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty((need,), dtype=torch.uint8).pin_memory()
+            self._pinned = buf
+        host = buf[:need].view(n, h, w, 3)
+        dst = host.numpy()
+        with torch.cuda.device(self.device):
+            dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+            step = max(1, (n + 3) // 4)
+            pool = getattr(self, "_copy_pool", None)
+            if pool is None and n >= 4:
+                from concurrent.futures import ThreadPoolExecutor
+                pool = self._copy_pool = ThreadPoolExecutor(max_workers=4)
+
+            def _cp(i):
+                dst[i] = frames[i]
+            for g0 in range(0, n, step):
+                g1 = min(n, g0 + step)
+                if pool is not None and g1 - g0 >= 2:
+                    list(pool.map(_cp, range(g0, g1)))
+                else:
+                    for i in range(g0, g1):
+                        dst[i] = frames[i]
+                dev[g0:g1].copy_(host[g0:g1], non_blocking=True)
+        return dev
+
     def run_frames(self, frames, keep_trace: bool = False) -> GroupResult:
         """Whole path for ``frames`` ``[n,H,W,3]`` uint8 (numpy: copied H2D; CUDA tensor: used in
         place).  Raises ValueError like the reference when no window can be extracted."""
