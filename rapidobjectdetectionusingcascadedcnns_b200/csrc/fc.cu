@@ -75,11 +75,26 @@ __global__ void __launch_bounds__(256) fc2_softmax_kernel(const float* __restric
     if (w >= n) return;
     const float* row = bott + w * ld;
     double s0 = 0.0, s1 = 0.0;
-    for (int k = lane; k < width; k += 32) {
-        const double v = (double)row[k];
-        const float2 wv = __ldg(reinterpret_cast<const float2*>(W2) + k);
-        s0 = fma(v, (double)wv.x, s0);
-        s1 = fma(v, (double)wv.y, s1);
+    if ((width & 127) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(bott) & 15) == 0) {
+        // 16-byte row loads (512 B per warp and instruction), all loads of a row in flight before the fp64 FMAs
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        const float4* w4 = reinterpret_cast<const float4*>(W2);          // [k][2] floats: two k per float4
+        #pragma unroll 4
+        for (int k4 = lane; k4 < width / 4; k4 += 32) {
+            const float4 v = row4[k4];
+            const float4 wa = __ldg(w4 + 2 * k4), wb = __ldg(w4 + 2 * k4 + 1);
+            s0 = fma((double)v.x, (double)wa.x, s0); s1 = fma((double)v.x, (double)wa.y, s1);
+            s0 = fma((double)v.y, (double)wa.z, s0); s1 = fma((double)v.y, (double)wa.w, s1);
+            s0 = fma((double)v.z, (double)wb.x, s0); s1 = fma((double)v.z, (double)wb.y, s1);
+            s0 = fma((double)v.w, (double)wb.z, s0); s1 = fma((double)v.w, (double)wb.w, s1);
+        }
+    } else {
+        for (int k = lane; k < width; k += 32) {
+            const double v = (double)row[k];
+            const float2 wv = __ldg(reinterpret_cast<const float2*>(W2) + k);
+            s0 = fma(v, (double)wv.x, s0);
+            s1 = fma(v, (double)wv.y, s1);
+        }
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

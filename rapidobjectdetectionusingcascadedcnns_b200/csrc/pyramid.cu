@@ -2,10 +2,10 @@
 // (data/image_info.py:201-250 via scipy.misc.imresize): horizontal pass -> u8 -> vertical pass
 // -> u8, 22-bit fixed-point coefficients precomputed on the host (plan.cu).
 //
-// Data movement: the horizontal kernel stages one source row in shared memory ONCE (planar per
-// channel) and emits that row of every level (so the frame is read once per batch, not once per
-// scale) with packed dp4a arithmetic; the vertical kernel streams the horizontal rows with
-// coalesced row-wise accesses.
+// Data movement: the horizontal kernel stages four source rows in shared memory ONCE (planar per
+// channel) and emits those rows of every level (so the frame is read once per batch, not once per
+// scale, and the coefficient table once per four rows) with packed dp4a arithmetic; the vertical
+// kernel streams the horizontal rows with coalesced row-wise accesses.
 #include "common.cuh"
 
 namespace rodc {
@@ -17,46 +17,63 @@ __device__ __forceinline__ uint8_t clip8(int acc) {
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// Horizontal pass.  grid: (H, n_frames); block: 256; dynamic smem: 3 planar channel rows of the source.
-// Work items are the (level, output x) pairs of ALL levels, flattened (so narrow levels do not idle
-// lanes).  The taps of an item are walked as aligned 4-pixel words: one LDS.32 per channel and word,
-// three __dp4a per channel (the 22-bit Pillow coefficient is split into three u8 limbs, so the integer
-// sum is exact: acc = a0 + (a1 << 8) + (a2 << 16)) -- ~1 instruction per multiply-add instead of 5.
+// Horizontal pass.  grid: (ceil(H / HROWS), n_frames); block: 256; dynamic smem: HROWS x 3 planar channel rows of
+// the source.  Work items are the (level, output x) pairs of ALL levels, flattened (so narrow levels do not idle
+// lanes).  The taps of an item are walked as aligned 4-pixel words: one LDS.32 per channel and word, three __dp4a
+// per channel (the 22-bit Pillow coefficient is split into three u8 limbs, so the integer sum is exact:
+// acc = a0 + (a1 << 8) + (a2 << 16)) -- ~1 instruction per multiply-add instead of 5.  A CTA handles HROWS source
+// rows so that every coefficient word (the 158 KB table is the same for all rows and streams from L2) is fetched
+// once per HROWS rows.
+constexpr int HROWS = 4;
 __global__ void __launch_bounds__(256) pyr_hpass_kernel(const uint8_t* __restrict__ frames, int H, int W,
                                                         const int32_t* __restrict__ items, int n_items,
                                                         const uint4* __restrict__ coef,
                                                         uint8_t* __restrict__ scratch, int64_t scratch_bytes) {
     extern __shared__ __align__(16) uint8_t rowsm[];
-    const int y = blockIdx.x, f = blockIdx.y;
+    const int y0 = blockIdx.x * HROWS, f = blockIdx.y;
     const int wpad = ((W + 3) & ~3) + 4;                    // words past W only ever meet zero coefficients
-    const uint8_t* src = frames + ((int64_t)f * H + y) * W * 3;
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-        const uint8_t* q = src + x * 3;
-        rowsm[x] = __ldg(q); rowsm[wpad + x] = __ldg(q + 1); rowsm[2 * wpad + x] = __ldg(q + 2);
+    for (int r = 0; r < HROWS; ++r) {
+        uint8_t* rs = rowsm + (size_t)r * 3 * wpad;
+        const int y = min(y0 + r, H - 1);                   // rows past H are computed from row H-1 and not stored
+        const uint8_t* src = frames + ((int64_t)f * H + y) * W * 3;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            const uint8_t* q = src + x * 3;
+            rs[x] = __ldg(q); rs[wpad + x] = __ldg(q + 1); rs[2 * wpad + x] = __ldg(q + 2);
+        }
+        for (int x = W + threadIdx.x; x < wpad; x += blockDim.x) { rs[x] = 0; rs[wpad + x] = 0; rs[2 * wpad + x] = 0; }
     }
-    for (int x = W + threadIdx.x; x < wpad; x += blockDim.x) { rowsm[x] = 0; rowsm[wpad + x] = 0; rowsm[2 * wpad + x] = 0; }
     __syncthreads();
-    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(rowsm);
-    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(rowsm + wpad);
-    const uint32_t* p2 = reinterpret_cast<const uint32_t*>(rowsm + 2 * wpad);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(rowsm);
+    const int wq = wpad / 4;                                // words per channel row
     uint8_t* sc = scratch + (int64_t)f * scratch_bytes;
     for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
         const int4 m = __ldg(reinterpret_cast<const int4*>(items) + it * 2);          // word0, n_words, coef word, out byte
         const int lw = __ldg(items + it * 8 + 4);
         const uint4* k = coef + m.z;
-        uint32_t a[3][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}};
+        uint32_t a[HROWS][3][3];
+        #pragma unroll
+        for (int r = 0; r < HROWS; ++r)
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { a[r][ch][0] = 0u; a[r][ch][1] = 0u; a[r][ch][2] = 0u; }
         for (int wi = 0; wi < m.y; ++wi) {
             const uint4 c = __ldg(k + wi);
-            const uint32_t v0 = p0[m.x + wi], v1 = p1[m.x + wi], v2 = p2[m.x + wi];
-            a[0][0] = __dp4a(v0, c.x, a[0][0]); a[0][1] = __dp4a(v0, c.y, a[0][1]); a[0][2] = __dp4a(v0, c.z, a[0][2]);
-            a[1][0] = __dp4a(v1, c.x, a[1][0]); a[1][1] = __dp4a(v1, c.y, a[1][1]); a[1][2] = __dp4a(v1, c.z, a[1][2]);
-            a[2][0] = __dp4a(v2, c.x, a[2][0]); a[2][1] = __dp4a(v2, c.y, a[2][1]); a[2][2] = __dp4a(v2, c.z, a[2][2]);
+            #pragma unroll
+            for (int r = 0; r < HROWS; ++r)
+                #pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const uint32_t v = p[(r * 3 + ch) * wq + m.x + wi];
+                    a[r][ch][0] = __dp4a(v, c.x, a[r][ch][0]); a[r][ch][1] = __dp4a(v, c.y, a[r][ch][1]); a[r][ch][2] = __dp4a(v, c.z, a[r][ch][2]);
+                }
         }
-        uint8_t* out = sc + m.w + (int64_t)y * lw * 3;
         #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const int acc = (int)(a[ch][0] + (a[ch][1] << 8) + (a[ch][2] << 16)) + (1 << (PREC_BITS - 1));
-            out[ch] = clip8(acc);
+        for (int r = 0; r < HROWS; ++r) {
+            if (y0 + r >= H) break;
+            uint8_t* out = sc + m.w + (int64_t)(y0 + r) * lw * 3;
+            #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int acc = (int)(a[r][ch][0] + (a[r][ch][1] << 8) + (a[r][ch][2] << 16)) + (1 << (PREC_BITS - 1));
+                out[ch] = clip8(acc);
+            }
         }
     }
 }
@@ -185,7 +202,7 @@ extern "C" int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, u
     const int nl = (int)p->levels.size();
     bool any_resample = false;
     for (auto& l : p->levels) any_resample |= !l.identity;
-    const size_t smem = (size_t)3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4);
+    const size_t smem = (size_t)HROWS * 3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4);
     if (any_resample && smem > 48 * 1024)
         RODC_CUDA(cudaFuncSetAttribute(pyr_hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t frame_bytes = (int64_t)p->img_h * p->img_w * 3;
@@ -195,7 +212,7 @@ extern "C" int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, u
         uint8_t* sc = scratch + (int64_t)f0 * p->scratch_bytes;
         uint8_t* py = pyramid + (int64_t)f0 * p->pyramid_bytes;
         if (any_resample) {
-            dim3 grid(p->img_h, nf);
+            dim3 grid((p->img_h + HROWS - 1) / HROWS, nf);
             pyr_hpass_kernel<<<grid, 256, smem, st>>>(fr, p->img_h, p->img_w, p->d_hitems, p->n_hitems,
                                                        reinterpret_cast<const uint4*>(p->d_hcoef), sc, p->scratch_bytes);
             RODC_LAUNCH_CHECK();
