@@ -442,32 +442,47 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
 // channels 4t..4t+3 of its group: stores are 8-byte, four lanes fill one 32-byte sector.  One
 // __syncthreads per window (input staging is double buffered).  This is also the producer the fused
 // feature->fc1 kernel needs (round 2): only the final store changes.
+// A warp row is VW = S x WPW pixels wide: one 48-px window, two 24-px windows side by side (lane groups 0-3 / 4-7:
+// every lane and every MMA row is used, the horizontal max simply does not look across the window boundary) or one
+// 12-px window (lane groups 6, 7 idle; packing four of them was measured slower: the extra per-lane state spills
+// inside the row loop).
 // Warp layout per window size (8 warps): S = 48 -> 1 window x 4 row parts x 2 channel groups;
-// S = 24 -> 2 windows x 2 parts x 2 groups; S = 12 -> 4 windows x 1 part x 2 groups, so small
+// S = 24 -> 2 warp slots x 2 windows x 2 parts x 2 groups; S = 12 -> 4 windows x 1 part x 2 groups, so small
 // windows are not dominated by the one-row halo that every row part recomputes.
-template <int S> struct StreamCfg { static constexpr int NQ = S >= 48 ? 4 : (S >= 24 ? 2 : 1); static constexpr int WPC = 4 / NQ; };
+template <int S> struct StreamCfg {
+    static constexpr int NQ = S >= 48 ? 4 : (S >= 24 ? 2 : 1);       // row parts per window
+    static constexpr int WPW = S == 24 ? 2 : 1;                       // windows side by side in one warp
+    static constexpr int WPC = (4 / NQ) * WPW;                        // windows per CTA iteration
+    // halves per staged fp16 window [P][P][4] (+ read slack); two windows of one warp are placed 16 banks apart so
+    // that the A-fragment loads of the two lane halves do not collide
+    static constexpr int INH0 = ((S + 2) * (S + 2) * 4 + 64 + 7) & ~7;
+    static constexpr int INH = WPW == 2 ? INH0 + ((16 - (INH0 / 2) % 32 + 32) % 32) * 2 : INH0;
+};
 
 template <int OUT_SPLIT, int S>
 __global__ void __launch_bounds__(FEAT_THREADS, 2)
 features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    constexpr int C = 32, P = S + 2, TR = (S + 15) / 16, NP = 2 * TR;    // NP pixels per thread and row
-    constexpr int NQ = StreamCfg<S>::NQ, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
-    constexpr int INH = (P * P * 4 + 64 + 7) & ~7;                       // halves per input buffer (+ read slack)
+    constexpr int NQ = StreamCfg<S>::NQ, WPW = StreamCfg<S>::WPW, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
+    constexpr int VW = S * WPW;                                           // pixels of a warp row
+    constexpr int C = 32, P = S + 2, TR = (VW + 15) / 16, NP = 2 * TR;   // NP pixels per thread and row
+    constexpr bool ALL_IN = 8 * NP == VW;                                 // every lane group owns pixels
+    static_assert(S % NP == 0 && VW <= 48, "a lane group lies inside one window or is idle");
+    constexpr int INH = StreamCfg<S>::INH;                               // halves per input buffer (+ read slack)
     constexpr int WIN_BYTES = S * S * 3, UPW = S * S / 4, UPI = WPC * UPW;   // 12-byte units (4 pixels) per window / iteration
-    constexpr bool ALL_IN = 8 * NP == S;                                 // every lane group owns pixels of the row
-    static_assert(S % NP == 0, "a lane group must be completely inside or outside the row");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* inh0 = reinterpret_cast<__half*>(smem_raw);                  // [2 buffers][WPC windows][INH]
     uint8_t* raw0 = smem_raw + (size_t)2 * WPC * INH * 2;                // [2 buffers][WPC windows][WIN_BYTES] u8 as fetched
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int cg = warp & 1, part = (warp >> 1) % NQ, slot = (warp >> 1) / NQ;
+    const int cg = warp & 1, part = (warp >> 1) % NQ;
+    const bool lane_in = ALL_IN || NP * g < VW;                           // S = 12 leaves lane groups 6, 7 idle
+    const int wsub = lane_in ? (NP * g) / S : 0;                          // this lane's window inside the warp
+    const int slot = ((warp >> 1) / NQ) * WPW + wsub;                    // ... and inside the CTA iteration
     const int ya = part * RQ;
-    const int xbase = NP * g;                                             // this thread's pixels: xbase .. xbase + NP - 1
-    const bool lane_in = xbase < S;                                      // S = 24 / 12 leave lane groups 6, 7 idle
+    const int xbase = lane_in ? NP * g - wsub * S : 0;                    // this thread's pixels: xbase .. xbase + NP - 1
 
     // B fragments of this warp's two n-tiles (permuted columns, bias folded into the spare K slot)
     uint32_t bf[3][2][2][2];
@@ -537,7 +552,8 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         __syncthreads();                                       // windows staged (and everyone left iteration iter - 1)
 
         const int64_t wrel = wrel0 + slot;
-        if (wrel >= n) continue;                               // tail: this warp's window slot is empty
+        if (wrel0 + (slot - wsub) >= n) continue;              // tail: all windows of this warp are beyond n
+        const bool live = lane_in && wrel < n;                 // idle lanes / lanes of a missing window compute along, never store
         const __half* inh = inhb + (size_t)slot * INH;
 
         // thread-constant output pointers (row offset added per row, pixel offsets are immediates)
@@ -546,11 +562,11 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         int64_t oofs = wrel * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
         asm volatile("" : "+l"(oofs));
         const int64_t lo_delta = OUT_SPLIT ? out_lo - out_hi : 0;
-        const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + (lane_in ? xbase : 0) * 4) + t;
+        const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + xbase * 4) + t;
         // lane / warp role flags in ONE register the compiler cannot rematerialise from %tid (S2R is a long-latency
         // read and was re-issued in every row): bit 0 left neighbour group, 1 right neighbour group, 2 first row
-        // part, 3 last row part, 4 lane owns pixels
-        int flags = (g > 0 ? 1 : 0) | (g < 7 ? 2 : 0) | (part == 0 ? 4 : 0) | (part == NQ - 1 ? 8 : 0) | (lane_in ? 16 : 0);
+        // part, 3 last row part, 4 the lane's window exists (stores allowed)
+        int flags = (lane_in && xbase > 0 ? 1 : 0) | (lane_in && xbase + NP < S ? 2 : 0) | (part == 0 ? 4 : 0) | (part == NQ - 1 ? 8 : 0) | (live ? 16 : 0);
         asm volatile("" : "+r"(flags));
         const bool has_left = flags & 1, has_right = flags & 2;
 
@@ -588,16 +604,15 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                             mma16816(acc[sub], a0, a1, a2, a3, bf[ky][sub][0][0], bf[ky][sub][0][1]);
                         }
                     }
-                    // S is a multiple of NP, so a lane group is either completely inside the row or idle (zeros
-                    // stand for the SAME padding); at S = 48 all eight groups are inside
-                    const bool in = ALL_IN || owns;
                     #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
-                        v[2 * j][2 * sub + 0] = in ? acc[sub][0] : 0.f;
-                        v[2 * j][2 * sub + 1] = in ? acc[sub][1] : 0.f;
-                        v[2 * j + 1][2 * sub + 0] = in ? acc[sub][2] : 0.f;
-                        v[2 * j + 1][2 * sub + 1] = in ? acc[sub][3] : 0.f;
+                        v[2 * j][2 * sub + 0] = acc[sub][0];
+                        v[2 * j][2 * sub + 1] = acc[sub][1];
+                        v[2 * j + 1][2 * sub + 0] = acc[sub][2];
+                        v[2 * j + 1][2 * sub + 1] = acc[sub][3];
                     }
+                    // values of idle lane groups are never looked at: their left neighbour is the last group of
+                    // the row, whose has_right flag is clear
                 }
                 // horizontal 3-max: only the first / last pixel of a thread need a neighbour lane
                 #pragma unroll
@@ -656,9 +671,7 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
 
 template <int S>
 static size_t feat3_smem_bytes() {
-    constexpr int P = S + 2;
-    constexpr int INH = (P * P * 4 + 64 + 7) & ~7;
-    return (size_t)2 * StreamCfg<S>::WPC * INH * 2 + (size_t)2 * StreamCfg<S>::WPC * S * S * 3;
+    return (size_t)2 * StreamCfg<S>::WPC * StreamCfg<S>::INH * 2 + (size_t)2 * StreamCfg<S>::WPC * S * S * 3;
 }
 
 static size_t feat2_smem_bytes(int S, int R) {
