@@ -192,10 +192,13 @@ def _stage_case(stage_idx, n=200, seed=0):
     return S, w, x, bott_in
 
 
+@pytest.mark.parametrize("n", [1, 37, 1187])       # single window; odd counts (half-filled window pairs at S = 24); > 1 CTA sweep
 @pytest.mark.parametrize("stage_idx", [0, 1, 2])
-def test_features_match_oracle(nat, stage_idx):
+def test_features_match_oracle(nat, stage_idx, n):
     from oracle import stage_net
-    S, w, x, _ = _stage_case(stage_idx, n=37)
+    if n > 1000 and stage_idx == 2:
+        n = 301                                      # keep the fp64 oracle within seconds at S = 48
+    S, w, x, _ = _stage_case(stage_idx, n=n)
     st = nat.Stage(w)
     feat = nat.stage_features(st, nat.make_source(dense=dev(x)), 0, x.shape[0], "cuda").cpu().numpy()
     _, _, _, ref = stage_net.stage_forward(x, w, None if stage_idx == 0 else np.zeros((x.shape[0], 512 * stage_idx), np.float32),
