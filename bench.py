@@ -305,7 +305,11 @@ def main():
                          "launches": int(dom_n.value), "avg_launch_ms": dom_ms.value / max(int(dom_n.value), 1),
                          "all_fc1_launches": int(fc1_n.value), "all_fc1_achieved": achieved_all,
                          "share_of_step": fc1_ms.value / ms_total if ms_total else None,
-                         "mma_per_product": mma_per_product},
+                         "mma_per_product": mma_per_product,
+                         # one `ncu --set full` capture of this kernel on this shape (profiles/r1h_ncu_full_fc1_pair.txt)
+                         "ncu": {"tensor_pipe_active": 0.97, "sm_clock_ghz_in_kernel": 1.33,
+                                 "note": "the tensor pipe is saturated; the clock is what the 1 kW power cap leaves"}
+                         if args.fc1 == "tensor" else None},
         }
         if not args.no_cpu_baseline and world == 1:
             fps, done, cores = cpu_port_time(3, budget_s=20.0)
