@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restri
     }
 }
 
+constexpr int ELIG_CAP = 1536;      // suppressing classes of a frame kept in shared memory (36 KB); more -> global scan
+
 // one block per frame: class numbering (order of first member = order of roots), sums, means,
 // filters, ordered per-frame output into tmp.
 __global__ void __launch_bounds__(1024) group_finalize_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ seg,
@@ -189,9 +191,29 @@ __global__ void __launch_bounds__(1024) group_finalize_kernel(const int32_t* __r
         for (int k = 0; k < 4; ++k) rrect[(int64_t)(s0 + c) * 4 + k] = __float2int_rn(__fmul_rn(__int2float_rn(sm[k]), s));
     }
     __syncthreads();
-    // 4. filters + ordered output
-    if (threadIdx.x == 0) carry = 0;
+    // 4. filters + ordered output.  Only classes with more than min_neighbors members can suppress another one
+    // (typically a tenth of all classes): their grown rectangles are collected in shared memory first, so the
+    // nested-rectangle test scans that short list instead of every class of the frame.
+    __shared__ int n_elig;
+    __shared__ int elig[ELIG_CAP][6];                          // class, x0 - dx, y0 - dy, x1 + dx, y1 + dy, members
+    if (threadIdx.x == 0) { carry = 0; n_elig = 0; }
     __syncthreads();
+    for (int c = threadIdx.x; c < ncls; c += 1024) {
+        const int n2 = sums[(int64_t)(s0 + c) * 5 + 4];
+        if (n2 > min_neighbors) {
+            const int slot = atomicAdd(&n_elig, 1);
+            if (slot < ELIG_CAP) {
+                const int32_t* r2 = rrect + (int64_t)(s0 + c) * 4;
+                const int dx = __double2int_rn(__dmul_rn((double)r2[2], eps));
+                const int dy = __double2int_rn(__dmul_rn((double)r2[3], eps));
+                elig[slot][0] = c; elig[slot][1] = r2[0] - dx; elig[slot][2] = r2[1] - dy;
+                elig[slot][3] = r2[0] + r2[2] + dx; elig[slot][4] = r2[1] + r2[3] + dy; elig[slot][5] = n2;
+            }
+        }
+    }
+    __syncthreads();
+    const bool use_list = n_elig <= ELIG_CAP;
+    const int n_list = n_elig;
     for (int base = 0; base < ncls; base += 1024) {
         const int c = base + threadIdx.x;
         int keep = 0, n1 = 0;
@@ -202,15 +224,24 @@ __global__ void __launch_bounds__(1024) group_finalize_kernel(const int32_t* __r
             r1 = make_int4(rr[0], rr[1], rr[2], rr[3]);
             if (n1 > min_neighbors) {
                 keep = 1;
-                for (int j = 0; j < ncls; ++j) {
-                    const int n2 = sums[(int64_t)(s0 + j) * 5 + 4];
-                    if (j == c || n2 <= min_neighbors) continue;
-                    const int32_t* r2 = rrect + (int64_t)(s0 + j) * 4;
-                    const int dx = __double2int_rn(__dmul_rn((double)r2[2], eps));
-                    const int dy = __double2int_rn(__dmul_rn((double)r2[3], eps));
-                    if (r1.x >= r2[0] - dx && r1.y >= r2[1] - dy &&
-                        r1.x + r1.z <= r2[0] + r2[2] + dx && r1.y + r1.w <= r2[1] + r2[3] + dy &&
-                        (n2 > max(3, n1) || n1 < 3)) { keep = 0; break; }
+                if (use_list) {
+                    for (int e = 0; e < n_list; ++e) {
+                        const int n2 = elig[e][5];
+                        if (elig[e][0] == c) continue;
+                        if (r1.x >= elig[e][1] && r1.y >= elig[e][2] && r1.x + r1.z <= elig[e][3] && r1.y + r1.w <= elig[e][4] &&
+                            (n2 > max(3, n1) || n1 < 3)) { keep = 0; break; }
+                    }
+                } else {
+                    for (int j = 0; j < ncls; ++j) {
+                        const int n2 = sums[(int64_t)(s0 + j) * 5 + 4];
+                        if (j == c || n2 <= min_neighbors) continue;
+                        const int32_t* r2 = rrect + (int64_t)(s0 + j) * 4;
+                        const int dx = __double2int_rn(__dmul_rn((double)r2[2], eps));
+                        const int dy = __double2int_rn(__dmul_rn((double)r2[3], eps));
+                        if (r1.x >= r2[0] - dx && r1.y >= r2[1] - dy &&
+                            r1.x + r1.z <= r2[0] + r2[2] + dx && r1.y + r1.w <= r2[1] + r2[3] + dy &&
+                            (n2 > max(3, n1) || n1 < 3)) { keep = 0; break; }
+                    }
                 }
             }
         }
