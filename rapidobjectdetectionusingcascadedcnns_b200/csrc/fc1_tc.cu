@@ -265,12 +265,17 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 //     smem-empty and tmem-full barriers of both CTAs
 //   - both CTAs drain their own TMEM half; the peer's epilogue warps arrive remotely on the leader's
 //     tmem-empty barrier (count 2 x EPI_WARPS)
-constexpr int STAGES2 = 3;
-constexpr int BN_HALF = BN / 2;
-constexpr int B_HALF_TILE = BN_HALF * BK * 2;              // 16 KB
-constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF_TILE; // 64 KB per CTA and k-block
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
-constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+// BN_ = 256 (3 stages x 64 KB) is the shape in use; the template also builds BN_ = 128 (4 stages x 48 KB).
+template <int BN_, int STAGES_> struct PairTile {
+    static constexpr int BN_HALF = BN_ / 2;
+    static constexpr int B_HALF_TILE = BN_HALF * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_HALF_TILE;       // per CTA and k-block
+    static constexpr int SMEM_BYTES = STAGES_ * STAGE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BN_;
+    static constexpr int N_TILES = FC1_N / BN_;
+    static constexpr int COLS_PER_WARP = BN_ / 2;
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
@@ -300,11 +305,15 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+template <int BN_, int STAGES_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
                float out_scale, int probe_hi_only) {
+    using T = PairTile<BN_, STAGES_>;
+    constexpr int STAGES2 = STAGES_, STAGE2_BYTES = T::STAGE_BYTES, BN_HALF = T::BN_HALF, B_HALF_TILE = T::B_HALF_TILE;
+    constexpr int CW = T::COLS_PER_WARP;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
@@ -318,9 +327,9 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
-    const int n_tile = pair & 1, m_pair = pair >> 1;
+    const int n_tile = pair % T::N_TILES, m_pair = pair / T::N_TILES;
     const int m0 = m_pair * (2 * BM) + (int)rank * BM;      // this CTA's 128 rows
-    const int n0 = n_tile * BN;
+    const int n0 = n_tile * BN_;
     const int num_chunks = (num_kb + kc - 1) / kc;
 
     if (threadIdx.x == 0) {
@@ -329,7 +338,7 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(T::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -375,7 +384,7 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
-                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN_);
                 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {                // the small cross terms first
                     const uint32_t koff = k * UMMA_K * 2;
@@ -383,13 +392,13 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const uint64_t a_lo = smem_desc_sw128(base + A_TILE + koff);
                     const uint64_t b_hi = smem_desc_sw128(base + 2 * A_TILE + koff);
                     const uint64_t b_lo = smem_desc_sw128(base + 2 * A_TILE + B_HALF_TILE + koff);
-                    umma_f16_2sm(acc, a_hi, b_lo, IDESC2, (kin | k) != 0);
-                    umma_f16_2sm(acc, a_lo, b_hi, IDESC2, 1u);
+                    umma_f16_2sm(acc, a_hi, b_lo, T::IDESC, (kin | k) != 0);
+                    umma_f16_2sm(acc, a_lo, b_hi, T::IDESC, 1u);
                 }
                 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {                // then the dominant hi*hi terms
                     const uint32_t koff = k * UMMA_K * 2;
-                    umma_f16_2sm(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), IDESC2, 1u);
+                    umma_f16_2sm(acc, smem_desc_sw128(base + koff), smem_desc_sw128(base + 2 * A_TILE + koff), T::IDESC, 1u);
                 }
                 umma_commit_2sm(smem_u32(&bar_empty[s]));              // smem slots of BOTH CTAs free
                 if (kin == kc - 1 || kb == num_kb - 1) umma_commit_2sm(smem_u32(&bar_tfull[buf]));
@@ -397,16 +406,16 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else {
         const int q = warp & 3, hcol = (warp - 2) >> 2;
-        float acc[128];
+        float acc[CW];
         #pragma unroll
-        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int j = 0; j < CW; ++j) acc[j] = 0.f;
         for (int chunk = 0; chunk < num_chunks; ++chunk) {
             const int buf = chunk & 1;
             mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(chunk >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hcol * 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_ + hcol * CW);
             #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CW / 32; ++c) {
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 #pragma unroll
@@ -418,10 +427,10 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         const int row = m0 + q * 32 + lane;
         if (row < m) {
-            float* orow = out + (int64_t)row * ld_out + n0 + hcol * 128;
-            const float* brow = bias + n0 + hcol * 128;
+            float* orow = out + (int64_t)row * ld_out + n0 + hcol * CW;
+            const float* brow = bias + n0 + hcol * CW;
             #pragma unroll
-            for (int j = 0; j < 128; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
                 float4 o;
                 o.x = fmaxf(fmaf(acc[j + 0], out_scale, __ldg(brow + j + 0)), 0.f);
                 o.y = fmaxf(fmaf(acc[j + 1], out_scale, __ldg(brow + j + 1)), 0.f);
@@ -434,7 +443,7 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                     // nobody exits while the pair still uses its smem / TMEM
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(T::TMEM_COLS) : "memory");
     }
 }
 
@@ -529,6 +538,8 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
     const unsigned m_tiles = (unsigned)((m + BM - 1) / BM);
     const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
     if (fc1_narrow_tiles(m_tiles)) {
+        // (a pair kernel with 128-wide tiles, PairTile<128, 4>, was measured slower here: 1.07 vs 0.82 ms at m = 3456 --
+        // with half the SMs' worth of CTAs the cluster handshakes outweigh the smaller operand stream)
         using T = Tile<128, 3>;
         if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
             (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, 128)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, 128))) return rc;
@@ -539,12 +550,13 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
         return RODC_OK;
     }
     if (fc1_use_2cta()) {
+        using P = PairTile<256, 3>;
         if ((rc = make_map(&ma_hi, a_hi, m, s->K, BM)) || (rc = make_map(&ma_lo, a_lo, m, s->K, BM)) ||
-            (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN_HALF)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN_HALF))) return rc;
-        RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-        const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * 2u;      // (M pairs) x (2 N tiles)
-        fc1_tc2_kernel<<<pairs * 2u, THREADS, SMEM2_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                 (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
+            (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, P::BN_HALF)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, P::BN_HALF))) return rc;
+        RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
+        const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * P::N_TILES;      // (M pairs) x (N tiles)
+        fc1_tc2_kernel<256, 3><<<pairs * 2u, THREADS, P::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
+                                                                           (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
