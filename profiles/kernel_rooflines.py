@@ -56,24 +56,30 @@ def main():
     alg = B * sum(3 * 640 * 480 + 3 * int(w) * int(h) for w, h in zip(plan.level_w, plan.level_h))
     row("K1 pyramid (h-pass + v-pass)", ms, alg, "SURVEY formula: source counted once per level; real DRAM traffic is ~4x lower")
 
-    # K2a per stage (stage 2 shape is the one that matters)
+    # K4 + K2a per stage on the product path: rodc_source_windows materialises the windows (pyramid crops at stage 0,
+    # cv2.resize re-crops after), the streaming feature kernel reads them densely (stage 2 shape is the one that matters)
     ws = synth.xavier_cascade()
+    from rapidobjectdetectionusingcascadedcnns_b200 import _lib
+    import ctypes as C
+    L = _lib.lib()
+    table = native.FrameTable.from_batch(frames)
     for i, (S, n) in enumerate([(12, B * plan.n_windows), (24, 37888), (48, 18944)]):
         st = native.Stage(ws[i])
-        meta = native.window_meta(plan, B, 0, dev)[:n].contiguous() if n <= B * plan.n_windows else None
-        table = native.FrameTable.from_batch(frames)
+        meta = native.window_meta(plan, B, 0, dev)[:n].contiguous()
         src = native.make_source(plan=plan, pyr=pyr) if i == 0 else native.make_source(table=table, meta=meta)
-        bott = torch.empty((n, st.width), dtype=torch.float32, device=dev)
-        wsb = torch.empty((n * st.K * 4,), dtype=torch.uint8, device=dev)
-        from rapidobjectdetectionusingcascadedcnns_b200 import _lib
-        import ctypes as C
-        L = _lib.lib()
-        # features only: the f32 test hook writes the same 4 B / feature as the split planes
-        feat = wsb.view(torch.float32).view(n, st.K)
-        ms = timeit(lambda: native._lib.check(L.rodc_stage_features_f32(st.handle, C.byref(src), 0, n, C.c_void_p(feat.data_ptr()),
+        res = {}
+
+        def copy_windows():
+            res["w"] = native.source_windows(src, 0, n, S, dev)
+        ms = timeit(copy_windows, flush, reps=10)
+        row("K4 window copy / re-crop S=%d (%d windows)" % (S, n), ms, n * S * S * 3,
+            "output bytes only; the re-crop is bound by the L1 sector rate of its scattered tap loads")
+        dsrc = native.make_source(dense=res["w"])
+        feat = torch.empty((n, st.K), dtype=torch.float32, device=dev)
+        ms = timeit(lambda: native._lib.check(L.rodc_stage_features_f32(st.handle, C.byref(dsrc), 0, n, C.c_void_p(feat.data_ptr()),
                                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))), flush, reps=10)
-        row("K2a features S=%d (%d windows)" % (S, n), ms, n * st.K * 4, "4 B per feature written")
-        del st, bott, wsb, feat
+        row("K2a features S=%d (%d windows)" % (S, n), ms, n * st.K * 4, "4 B per feature written (pure write stream: compare with the 6.3-7.0 TB/s write-only rate)")
+        del st, feat, res, dsrc
 
     # K3 on stage-0 sized input with bottleneck gather
     n = B * plan.n_windows
