@@ -30,7 +30,6 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE = BM * BK * 2;                 // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr int TMEM_COLS = 512;                 // two 128 x 256 fp32 accumulator buffers (2-CTA variant)
 
 // Tile configuration of the 1-CTA kernel.  BN_ = 256 (2 smem stages of 96 KB) is the throughput shape;
 // BN_ = 128 (3 stages of 64 KB) doubles the CTA count for small m, where a 256-wide grid leaves SMs idle
