@@ -149,8 +149,8 @@ int  rodc_stage_create_general(int in_size, int n_conv, const int32_t* channels,
 void rodc_stage_destroy(rodc_stage* s);
 
 #define RODC_SRC_DENSE   0   /* windows already materialised: dense [n,S,S,3] u8            */
-#define RODC_SRC_PYRAMID 1   /* stage 0: read windows in place from the packed pyramid       */
-#define RODC_SRC_RECROP  2   /* stages >=1: crop+resize on the fly from the original frames  */
+#define RODC_SRC_PYRAMID 1   /* stage 0: windows inside the packed pyramid (K1 output)       */
+#define RODC_SRC_RECROP  2   /* stages >=1: crop + cv2.resize from the original frames       */
 #define RODC_SRC_GATHER  3   /* stage 0 over frames of DIFFERENT shapes: per-window byte offset + */
                              /* row pitch into one buffer holding several packed pyramids          */
 typedef struct {
@@ -168,14 +168,18 @@ typedef struct {
 } rodc_window_source;
 
 #define RODC_IMPL_TENSOR 0   /* tcgen05 split-fp16 GEMM (3 MMAs, fp32-grade)                 */
-#define RODC_IMPL_SIMT   1   /* The u8 input of a stage for any window source: out [n,size,size,3] u8 = the reference's windows_raw
- * slice fed to X (inference_cascade_app.py:200-202).  API / parity path (the stage kernels read the sources
- * in place); for RODC_SRC_PYRAMID it equals rodc_extract_windows, for RODC_SRC_RECROP rodc_recrop. */
+#define RODC_IMPL_SIMT   1   /* fp32 CUDA-core GEMM (cross-check implementation)             */
+
+/* The u8 input of a stage for any window source: out [n,size,size,3] u8 = the reference's windows_raw
+ * slice fed to X (inference_cascade_app.py:200-202).  rodc_stage_forward runs the same kernels per chunk
+ * into its workspace before the streaming feature kernel (the generic feature kernels read every source in
+ * place); for RODC_SRC_PYRAMID it equals rodc_extract_windows, for RODC_SRC_RECROP rodc_recrop. */
 int rodc_source_windows(const rodc_window_source* src, int64_t first, int64_t n, int size, uint8_t* out,
                         void* stream);
 
-/* fp32 CUDA-core GEMM (cross-check implementation)             */
-
+/* Bytes of workspace rodc_stage_forward wants for n windows: per window of a chunk 4*K bytes of features
+ * (two fp16 planes or one fp32 plane) + size*size*3 bytes of materialised u8 input; smaller workspaces
+ * are legal and make the call run in more chunks. */
 int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, int impl);
 /* Forward of windows [first, first+n) of `src`.
  *   bottleneck [n, ld_bott] f32: columns [0,fc1_size) are written; columns
