@@ -123,7 +123,9 @@ int rodc_window_scaled_rows(const int32_t* meta, const int32_t* slot, int64_t n,
  * cv2.resize(window.raw_norm, (size,size)), INTER_LINEAR 8U fixed point incl. the 2x
  * INTER_AREA shortcut, bit-exact.
  *   frames_base + frame_off[f] -> [frame_hw[f][0], frame_hw[f][1], 3] u8
- *   meta [n,5] as above        out [n, size, size, 3] u8 */
+ *   meta [n,5] as above        out [n, size, size, 3] u8
+ * The kernel fetches taps with aligned 8-byte loads: it may read up to 7 bytes around a frame byte inside
+ * that byte's aligned 8-byte word, i.e. never outside the 256-byte allocation granule of device memory. */
 int rodc_recrop(const uint8_t* frames_base, const int64_t* frame_off, const int32_t* frame_hw,
                 const int32_t* meta, int64_t n, int size, uint8_t* out, void* stream);
 
