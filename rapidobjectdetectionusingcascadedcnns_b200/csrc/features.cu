@@ -453,6 +453,7 @@ template <int S> struct StreamCfg {
     static constexpr int NQ = S >= 48 ? 4 : (S >= 24 ? 2 : 1);       // row parts per window
     static constexpr int WPW = S == 24 ? 2 : 1;                       // windows side by side in one warp
     static constexpr int WPC = (4 / NQ) * WPW;                        // windows per CTA iteration
+    static constexpr int CTAS_PER_SM = S == 12 ? 3 : 2;               // the 12-px kernel needs < 86 registers
     // halves per staged fp16 window [P][P][4] (+ read slack); two windows of one warp are placed 16 banks apart so
     // that the A-fragment loads of the two lane halves do not collide
     static constexpr int INH0 = ((S + 2) * (S + 2) * 4 + 64 + 7) & ~7;
@@ -460,7 +461,7 @@ template <int S> struct StreamCfg {
 };
 
 template <int OUT_SPLIT, int S>
-__global__ void __launch_bounds__(FEAT_THREADS, 2)
+__global__ void __launch_bounds__(FEAT_THREADS, StreamCfg<S>::CTAS_PER_SM)
 features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
@@ -879,7 +880,8 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         do {                                                                                                              \
             const size_t smem = feat3_smem_bytes<ST_>();                                                                  \
             RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            features_stream_kernel<SPLIT, ST_><<<grid, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,     \
+            const unsigned g3 = (unsigned)(n < 148 * StreamCfg<ST_>::CTAS_PER_SM ? n : 148 * StreamCfg<ST_>::CTAS_PER_SM);  \
+            features_stream_kernel<SPLIT, ST_><<<g3, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,       \
                                                                                  ldexpf(1.f, s->a_exp - s->c_exp),          \
                                                                                  ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo); \
         } while (0)
