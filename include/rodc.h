@@ -197,7 +197,8 @@ int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, 
 
 /* ---------------------------------------------------------------- K3 compaction
  * Replaces the per-row Python filter (inference_cascade_app.py:219-247): keep window w iff
- * (double)probs[w,1] > threshold (strict), order preserved; gathers metadata rows, the
+ * (double)probs[w,1] > threshold (strict; threshold = NaN selects the single-net rule
+ * argmax != background, i.e. probs[w,1] > probs[w,0], inference_app.py:140-149), order preserved; gathers metadata rows, the
  * bottleneck rows (into columns [col_off, col_off+width) of bott_out) and the confidence
  * (mode 0 = p, 1 = acc + p, 2 = acc * p).  count_out (device int64) receives the number
  * kept; keep_idx_out [<=n] i32 the kept positions.  scratch: rodc_compact_scratch_bytes(n). */
@@ -219,16 +220,26 @@ int64_t rodc_group_scratch_bytes(int64_t k, int n_frames);
 int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
                           int32_t* out, int64_t* out_count, void* scratch, void* stream);
 
-/* ---------------------------------------------------------------- measurement hook
- * When enabled, every fc1 launch (the dominant kernel) is bracketed by cudaEvents on the stream it
- * is launched on.  rodc_profile_collect synchronises those events and returns the summed device
- * time, the algorithmic FLOPs (2*m*K*N per launch) and the launch count since the last collect --
- * once over all fc1 launches and once over the launches of the dominant shape (largest FLOP count,
- * i.e. full stage-2 chunks), which is what the roofline is quoted on.
- * This is the library's only process-wide state; it is off by default. */
-int rodc_profile_enable(int on);
+/* ---------------------------------------------------------------- launch accounting + measurement hook
+ * rodc_launch_count: kernel launches the library has issued since it was loaded (monotonic, process wide).
+ * bench.py reports the difference of two reads around its timed region as "gpu_launches".
+ *
+ * rodc_profile_enable(level): 0 = off (default); 1 = every fc1 launch (the dominant kernel) is bracketed by
+ * cudaEvents on the stream it is launched on; 2 = every kernel class is.  rodc_profile_collect synchronises
+ * the recorded events and returns the summed device time, the algorithmic FLOPs (2*m*K*N per launch) and the
+ * launch count of fc1 since the last collect -- once over all fc1 launches and once over the launches of the
+ * dominant shape (largest FLOP count, i.e. full stage-2 chunks), which is what the roofline is quoted on.
+ * rodc_profile_table then returns one row per (kernel class, window side) seen by that collect: summed device
+ * ms, algorithmic bytes and FLOPs by SURVEY.md §8(d)'s definitions, kernel launches and recorded scopes;
+ * the return value is the number of rows written (<= max_rows).  rodc_kernel_class_name names a class.
+ * The counters and the record list are the library's only process-wide state. */
+int64_t     rodc_launch_count(void);
+const char* rodc_kernel_class_name(int kernel_class);
+int rodc_profile_enable(int level);
 int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches,
                          double* dom_ms, double* dom_flops, int64_t* dom_launches);
+int rodc_profile_table(int max_rows, int32_t* kernel_class, int32_t* window_side, double* ms, double* bytes,
+                       double* flops, int64_t* launches, int64_t* records);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,9 @@ SIGNATURES = {
     "rodc_group_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int]),
     "rodc_profile_enable": (C.c_int, [C.c_int]),
     "rodc_profile_collect": (C.c_int, [c_f64p, c_f64p, c_i64p, c_f64p, c_f64p, c_i64p]),
+    "rodc_profile_table": (C.c_int, [C.c_int, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_i64p, c_i64p]),
+    "rodc_launch_count": (C.c_int64, []),
+    "rodc_kernel_class_name": (C.c_char_p, [C.c_int]),
     "rodc_group_rectangles": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp]),
 }
 
@@ -82,13 +85,27 @@ class RodcError(RuntimeError):
     pass
 
 
+_PATH_OVERRIDE = None
+
+
+def use_library(path: str) -> None:
+    """Point the binding at another build of the same ABI BEFORE the first call (``profiles/`` scripts load
+    ``librodc_probes.so`` this way).  A code-level switch on purpose: no environment variable can swap the
+    library under a user of the package."""
+    global _PATH_OVERRIDE
+    if _LIB is not None:
+        raise RodcError("use_library() must be called before the library is loaded")
+    _PATH_OVERRIDE = path
+
+
 def lib() -> C.CDLL:
-    """Load (building first if needed) librodc.so and declare every signature."""
+    """Load librodc.so and declare every signature.  The library is (re)built first whenever its content stamp
+    does not match the sources in ``csrc/`` -- a stale ``.so`` is never used silently."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB
-        if not os.path.exists(path) or os.environ.get("RODC_REBUILD"):
-            _build.build_library()
+        path = _PATH_OVERRIDE or _build.LIB
+        if _PATH_OVERRIDE is None and (not _build.is_current() or os.environ.get("RODC_REBUILD")):
+            _build.build_library(force=bool(os.environ.get("RODC_REBUILD")))
         handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the .so does not export it

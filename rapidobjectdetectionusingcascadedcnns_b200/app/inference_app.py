@@ -12,6 +12,7 @@ import numpy as np
 
 from .. import config as cf
 from ..data.db import label
+from ..data.box_list import BoxList
 from ..data.rectangles import LabeledBoundingBox, Window
 from ..network.stage_model import StageModel, model_paths
 from ..utils import log
@@ -115,29 +116,26 @@ class InferenceApp(AbstractInferenceApp):
 
     # ------------------------------------------------------------------ results
     @staticmethod
-    def _boxes_from_result(res, infos, n_frames: int) -> List[List[LabeledBoundingBox]]:
+    def _boxes_from_result(res, infos, n_frames: int, flat: bool = False):
+        """Per-frame ``BoxList`` views of the result arrays (objects are created on first use).  ``flat=True``
+        returns ONE list over all frames in result order (``run_inference_on_windows`` without NMS)."""
         fg = label.get_by_iid(label.IID_FOREGROUND)
         post_nms = cf.get("nms") == cf.NMS_OPENCV
-        out = [[] for _ in range(n_frames)]
-        frames = res.frame.tolist()
-        # thousands of boxes per batch: objects are filled slot by slot without the __init__ call frame (1/3 cheaper)
-        new, cls = LabeledBoundingBox.__new__, LabeledBoundingBox
-        if post_nms:          # numpy ints and float(weight) like `:203-212`
-            bx = res.boxes
-            for f, x0, y0, x1, y1, c in zip(frames, list(bx[:, 0]), list(bx[:, 1]), list(bx[:, 2]), list(bx[:, 3]),
-                                            res.conf.tolist()):
-                o = new(cls)
-                o._xmin = x0; o._ymin = y0; o._xmax = x1; o._ymax = y1
-                o._label = fg; o._confidence = c; o._image = infos[f]
-                out[f].append(o)
-        else:                 # python ints and the float32 softmax like cascade `:319-334`
-            for f, b, c in zip(frames, res.boxes.tolist(), res.conf):
-                o = new(cls)
-                o._xmin, o._ymin, o._xmax, o._ymax = b
-                o._label = fg; o._confidence = c; o._image = infos[f]
-                out[f].append(o)
-        if cf.get("vertically_enlarge_bboxes"):
-            out = [LabeledBoundingBox.vertically_enlarge_bboxes(bs) if bs else bs for bs in out]
+        enlarge = bool(cf.get("vertically_enlarge_bboxes"))
+        frames = np.asarray(res.frame)
+        if flat:
+            bl = BoxList(res.boxes, res.conf, [infos[f] for f in frames.tolist()], fg, post_nms)
+            return LabeledBoundingBox.vertically_enlarge_bboxes(bl) if enlarge and len(bl) else bl
+        # frame ids ascend (K5 emits frame by frame, compaction is stable): one slice per frame
+        cuts = np.searchsorted(frames, np.arange(n_frames + 1), side="left").tolist()
+        out = []
+        for f in range(n_frames):
+            a, b = cuts[f], cuts[f + 1]
+            if a == b:
+                out.append([])
+                continue
+            bl = BoxList(res.boxes[a:b], res.conf[a:b], infos[f], fg, post_nms)
+            out.append(LabeledBoundingBox.vertically_enlarge_bboxes(bl) if enlarge else bl)
         return out
 
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
@@ -194,11 +192,16 @@ class InferenceApp(AbstractInferenceApp):
         # Window.scale / Window.width feed the resize-then-crop branch (inference_cascade_app.py:358-359)
         scales = np.asarray([wi.scale for wi in windows_info], np.float64)
         widths = np.asarray([wi.width for wi in windows_info], np.int64)
-        if (np.diff(meta[:, 0]) < 0).any():            # the device NMS wants candidates grouped by frame
+        post_nms = cf.get("nms") == cf.NMS_OPENCV
+        if post_nms and (np.diff(meta[:, 0]) < 0).any():    # the device NMS wants candidates grouped by frame
             order = np.argsort(meta[:, 0], kind="stable")
             meta, raw, scales, widths = meta[order], raw[order], scales[order], widths[order]
         res = self._engine.run_windows(raw, meta, frames, scales=scales, widths=widths)
         self._log_stage_stats(res)
+        if not post_nms:
+            # without NMS the reference returns the survivors in the order of the given windows, also when the
+            # windows of several images are interleaved (`:135-154`, cascade `:319-334`)
+            return self._boxes_from_result(res, infos, len(infos), flat=True)
         per_frame = self._boxes_from_result(res, infos, len(infos))
         return [b for boxes in per_frame for b in boxes]
 

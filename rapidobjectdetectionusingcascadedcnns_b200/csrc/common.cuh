@@ -25,6 +25,26 @@ void set_error(const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Kernel classes of the launch accounting / measurement hook (prof.cu, rodc_profile_table).
+enum KernelClass { KC_PYR_H = 0, KC_PYR_V, KC_WINTAB, KC_SOURCE, KC_RECROP, KC_FEAT, KC_FC1, KC_FC1_SIMT, KC_FC2,
+                   KC_COMPACT, KC_GROUP, KC_MISC, KC_COUNT };
+
+// Scope around the launch(es) of one kernel class: counts them (rodc_launch_count) and, when profiling is on,
+// brackets them with cudaEvents on `st`.  `bytes` / `flops` are the algorithmic figures of SURVEY.md §8(d).
+int profile_level();
+class Prof {
+public:
+    Prof(int kc, cudaStream_t st, int sub = 0, double bytes = 0.0, double flops = 0.0, int launches = 1);
+    ~Prof();
+    // device accumulator (one u64) for a data-dependent pixel count, NULL unless this scope is being recorded;
+    // 3 bytes per counted pixel are added to the scope's bytes at collect time
+    unsigned long long* area_slot();
+    bool recording() const { return rec_ >= 0; }
+private:
+    cudaStream_t st_;
+    int rec_;
+};
+
 struct LevelInfo {            // one pyramid level of a plan (host + device copies)
     double  scale;
     int32_t w, h;             // level size

@@ -14,8 +14,13 @@ namespace rodc {
 
 constexpr int CT = 1024;     // windows per tile (one block of 1024 threads, one window per thread)
 
+// thr == NaN selects the single-net rule of app/inference_app.py:140-149: keep iff np.argmax(p) != 0, i.e.
+// p[1] > p[0] (a tie goes to index 0 = background) -- not the same as p[1] > 0.5 when fp32 rounding gives
+// p[1] == 0.5 > p[0].
 __device__ __forceinline__ bool keep_pred(const float* probs, int64_t w, int64_t n, double thr) {
-    return w < n && (double)probs[2 * w + 1] > thr;
+    if (w >= n) return false;
+    if (thr != thr) return probs[2 * w + 1] > probs[2 * w];
+    return (double)probs[2 * w + 1] > thr;
 }
 
 __global__ void __launch_bounds__(CT) compact_count_kernel(const float* __restrict__ probs, int64_t n, double thr,
@@ -137,9 +142,16 @@ extern "C" int rodc_compact(const float* probs, int64_t n, double threshold,
         RODC_CHECK_ARG(bott_out && keep_idx_out, "rodc_compact: bottleneck gather needs bott_out and keep_idx_out");
         RODC_CHECK_ARG(width % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && col_off % 4 == 0,
                        "rodc_compact: bottleneck widths/strides must be multiples of 4 floats");
+        RODC_CHECK_ARG(width > 0 && width <= ld_in && col_off >= 0 && col_off + width <= ld_out,
+                       "rodc_compact: bottleneck row [%d, %d) does not fit the rows (ld_in %d, ld_out %d)",
+                       col_off, col_off + width, ld_in, ld_out);
     }
     int32_t* tile = reinterpret_cast<int32_t*>(scratch);
     const int nt = (int)((n + CT - 1) / CT);
+    // 8 n (score reads of the two passes) + per survivor 24 B (meta + index) + 8 D_i (row gather, r + w).
+    // The survivor count is data dependent: bytes are booked for the worst case n survivors of the gather.
+    Prof prof(KC_COMPACT, st, width, 8.0 * (double)n + (double)n * 44.0 + (bott_in ? 8.0 * (double)n * width : 0.0), 0.0,
+              bott_in ? 4 : 3);
     compact_count_kernel<<<nt, CT, 0, st>>>(probs, n, threshold, tile);
     RODC_LAUNCH_CHECK();
     compact_scan_kernel<<<1, 1024, 0, st>>>(tile, nt, count_out);

@@ -116,6 +116,8 @@ int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bo
     RODC_CHECK_ARG(s->fc1_size % 128 == 0, "fc1_size must be a multiple of 128 (got %d)", s->fc1_size);
     RODC_CHECK_ARG(s->K % 8 == 0, "K must be a multiple of 8");
     dim3 grid(s->fc1_size / 128, (unsigned)((m + 127) / 128));
+    Prof prof(KC_FC1_SIMT, st, s->in_size, (double)m * (double)s->K * 4.0 + (double)s->K * s->fc1_size * 4.0 + (double)m * s->fc1_size * 4.0,
+              2.0 * (double)m * (double)s->K * (double)s->fc1_size);
     fc1_simt_kernel<<<grid, 256, 0, st>>>(feat, s->fc1_w, s->fc1_b, bott, ld_bott, m, s->K, s->fc1_size);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
@@ -125,6 +127,8 @@ int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int6
     if (n <= 0) return RODC_OK;
     const int width = s->fc1_size + s->n_prev;
     const int wpb = 8;
+    // K2c: reads the [own | prev] bottleneck row, writes logits + softmax (4 * 512 (i + 1) B / window)
+    Prof prof(KC_FC2, st, s->in_size, (double)n * (4.0 * width + 16.0), (double)n * 4.0 * width);
     fc2_softmax_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(bott, ld_bott, width, n, s->fc2_w, s->fc2_b, logits, probs);
     RODC_LAUNCH_CHECK();
     return RODC_OK;

@@ -166,12 +166,14 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bar_full[s]);
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+#ifdef RODC_PROBES
                 if (probe_hi_only) {            // bandwidth probe (wrong numerics): half the bytes, same MMAs
                     mbar_expect_tx(full, A_TILE + B_TILE);
                     tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
                     tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
                     continue;
                 }
+#endif
                 mbar_expect_tx(full, STAGE_BYTES);
                 tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
                 tma_load_2d(base + A_TILE, &map_a_lo, full, kb * BK, m0);
@@ -357,6 +359,7 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                 const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[s]), 0);
                 const uint32_t base = smem_u32(smem + s * STAGE2_BYTES);
+#ifdef RODC_PROBES
                 if (probe_hi_only) {            // bandwidth probe (wrong numerics)
                     if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * (A_TILE + B_HALF_TILE));
                     else mbar_arrive_cluster(full_leader);
@@ -364,6 +367,7 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
                     continue;
                 }
+#endif
                 if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * STAGE2_BYTES);   // both CTAs' bytes land here
                 else mbar_arrive_cluster(full_leader);
                 tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
@@ -476,12 +480,14 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
     return RODC_OK;
 }
 
-// k-blocks (of 64) accumulated inside the tensor core before a drain; RODC_FC1_KC overrides (tests).
+// k-blocks (of 64) accumulated inside the tensor core before a drain.  The value changes the rounding of the
+// result, so the shipped library fixes it; only a -DRODC_PROBES build (profiles/ experiments) reads RODC_FC1_KC.
 // Measured on B200 against the fp64 oracle (profiles/r1h_fc1_precision.txt), max |margin error| per stage:
 //   kc = 1: 5.3e-5 / 6.8e-5 / 7.1e-5     kc = 2: 6.1e-5 / 9.4e-5 / 6.2e-5     kc = 4: 7.6e-5 / 1.25e-4 / 1.0e-4
 // kc = 2 is indistinguishable from kc = 1 (the floor is the fp32 rounding of fc2 / the register sums) and
 // halves the TMEM drains and their barrier round trips, which the pair kernel needs to run ahead.
 static int fc1_chunk_kblocks() {
+#ifdef RODC_PROBES
     static int kc = 0;
     if (kc == 0) {
         const char* e = getenv("RODC_FC1_KC");
@@ -489,6 +495,9 @@ static int fc1_chunk_kblocks() {
         if (kc < 1) kc = 1;
     }
     return kc;
+#else
+    return 2;
+#endif
 }
 
 // Kernel choice.  fc1 alone, stage 2, m = 18944 (two waves), B200 burst timing (profiles/r1h_fc1_variants.jsonl):
@@ -496,18 +505,27 @@ static int fc1_chunk_kblocks() {
 //   pair   256x256 tiles, kc 1: 3.42 ms      kc 2: 2.77 ms      kc 4: 2.69 ms
 // The single-CTA kernel is bound by the L2 -> SM operand stream (96 KB per k-block and SM, ~10 TB/s chip wide),
 // not by the tensor pipe; the pair kernel streams 64 KB per k-block and SM and wins once its cross-CTA drain
-// handshake happens every second k-block.  It is the default; RODC_FC1_2CTA=0 selects the single-CTA kernel.
+// handshake happens every second k-block.  It is the default; RODC_FC1_2CTA=0 selects the single-CTA kernel
+// (bit-identical results: every output element sees the same k order, tests/test_gpu_kernels.py).
 static bool fc1_use_2cta() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RODC_FC1_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 
-// RODC_FC1_PROBE_HI_ONLY=1: measurement aid only -- loads half the operand bytes (results are WRONG)
+// -DRODC_PROBES builds only: RODC_FC1_PROBE_HI_ONLY=1 loads half the operand bytes (a bandwidth probe whose
+// results are WRONG).  The shipped library does not contain the path.
 static int fc1_probe_hi_only() {
+#ifdef RODC_PROBES
     static int v = -1;
-    if (v < 0) { const char* e = getenv("RODC_FC1_PROBE_HI_ONLY"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) {
+        const char* e = getenv("RODC_FC1_PROBE_HI_ONLY"); v = (e && e[0] == '1') ? 1 : 0;
+        if (v) fprintf(stderr, "librodc: RODC_FC1_PROBE_HI_ONLY is active -- fc1 results are WRONG (probe build)\n");
+    }
     return v;
+#else
+    return 0;
+#endif
 }
 
 // 128-wide N tiles when the 256-wide grid (2 CTAs per 128 rows) cannot fill the 148 SMs even once.
@@ -534,6 +552,9 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
     RODC_CHECK_ARG((reinterpret_cast<uintptr_t>(bott) & 15) == 0, "bottleneck buffer must be 16-byte aligned");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
+    // algorithmic bytes: the A operand once (4 B / feature as materialised), the weights once, the output once
+    Prof prof(KC_FC1, st, s->in_size, (double)m * (double)s->K * 4.0 + (double)s->K * FC1_N * 4.0 + (double)m * FC1_N * 4.0,
+              2.0 * (double)m * (double)s->K * (double)FC1_N);
     const unsigned m_tiles = (unsigned)((m + BM - 1) / BM);
     const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
     if (fc1_narrow_tiles(m_tiles)) {

@@ -832,9 +832,28 @@ int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out) {
     return RODC_OK;
 }
 
+// measurement only (profile level 2): sum of the survivors' crop areas, the data-dependent term of K4's
+// algorithmic bytes 3 (w_n h_n + S^2) per survivor
+__global__ void __launch_bounds__(256) crop_area_kernel(SrcDev src, int64_t first, int64_t n, unsigned long long* __restrict__ acc) {
+    unsigned long long a = 0;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n; w += (int64_t)gridDim.x * blockDim.x) {
+        const Crop c = make_crop(src, first + w);
+        a += (unsigned long long)max(c.sw, 0) * (unsigned long long)max(c.sh, 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0 && a) atomicAdd(acc, a);
+}
+
 int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st) {
     if (n <= 0) return RODC_OK;
     const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
+    const bool rc_src = src.kind == RODC_SRC_RECROP;
+    // stage-0 copy: window bytes read + written; K4: 3 S^2 written per survivor + 3 w_n h_n read (added below)
+    Prof prof(rc_src ? KC_RECROP : KC_SOURCE, st, size, (rc_src ? 1.0 : 2.0) * (double)n * size * size * 3, 0.0);
+    if (rc_src && prof.recording()) {
+        if (unsigned long long* acc = prof.area_slot())
+            crop_area_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(src, first, n, acc);
+    }
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
     if (aligned && src.kind == RODC_SRC_RECROP && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out);
     else if (aligned && src.kind == RODC_SRC_RECROP && size == 24) recrop_windows_kernel<24, 24><<<grid, 144, 0, st>>>(src, first, n, out);
@@ -855,6 +874,7 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         for (int l = 0; l < 8; ++l) { net.chan[l] = s->chan[l]; net.w[l] = s->gconv_w[l]; net.b[l] = s->gconv_b[l]; }
         const unsigned grid = (unsigned)(n < GENERAL_CTAS ? n : GENERAL_CTAS);
         const size_t smem = (size_t)6 * s->in_size * sizeof(int);
+        Prof prof(KC_FEAT, st, s->in_size, (double)n * ((double)s->in_size * s->in_size * 3 + 4.0 * (double)s->K), 0.0);
         if (out_f32) features_general_kernel<0><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
                                                                                   1.f, out_f32, nullptr, nullptr, s->K);
         else features_general_kernel<1><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
@@ -866,6 +886,9 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
     RODC_CHECK_ARG((s->in_size & 3) == 0, "stage input size must be a multiple of 4 (got %d)", s->in_size);
     RODC_CHECK_ARG(n < (1ll << 31), "too many windows in one launch");
     const int S = s->in_size;
+    // bytes: the u8 window in, 4 B per feature out (the materialised fc1 operand -- design traffic, not part of
+    // SURVEY §8d's algorithmic bytes of K2, whose bound is the tensor pipe); flops: the 3x3x3 -> 32 conv
+    Prof prof(KC_FEAT, st, S, (double)n * ((double)S * S * 3 + 4.0 * (double)s->K), 2.0 * 27.0 * (double)n * (double)s->K);
     const float a_scale = ldexpf(1.f, s->a_exp);
     const float conv_scale = ldexpf(1.f, -s->c_exp);
     // persistent-style grid: two CTAs per SM, each loops over windows

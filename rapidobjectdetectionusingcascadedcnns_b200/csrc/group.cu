@@ -337,11 +337,14 @@ extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frame
     RODC_CHECK_ARG(cand && out && scratch && n_frames > 0, "rodc_group_rectangles: NULL argument");
     int blocks = (int)((k + 255) / 256);
     if (min_neighbors <= 0) {
+        Prof prof(KC_GROUP, st, 0, 44.0 * (double)k, 0.0);
         group_passthrough_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(cand, k, out, out_count);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
     GroupScratch g = carve(scratch, k, n_frames);
+    // 20 K (candidates) + 24 K' (groups, K' <= K); the K^2 / 2 predicate evaluations are ALU work
+    Prof prof(KC_GROUP, st, 0, 44.0 * (double)k, 0.0, 6);
     group_segments_kernel<<<(n_frames + 1 + 255) / 256, 256, 0, st>>>(cand, k, n_frames, g.seg);
     RODC_LAUNCH_CHECK();
     group_init_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(g.parent, g.sums, k);

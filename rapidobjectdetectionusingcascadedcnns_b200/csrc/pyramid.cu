@@ -211,13 +211,19 @@ extern "C" int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, u
         const uint8_t* fr = frames + (int64_t)f0 * frame_bytes;
         uint8_t* sc = scratch + (int64_t)f0 * p->scratch_bytes;
         uint8_t* py = pyramid + (int64_t)f0 * p->pyramid_bytes;
+        // SURVEY §8d books K1 as sum over levels of (3 W H source read + 3 w_k h_k level write) per frame: the h-pass
+        // gets the source term, the v-pass the level term
+        double lv_bytes = 0.0; int n_res = 0;
+        for (auto& l : p->levels) { lv_bytes += 3.0 * l.w * l.h; n_res += l.identity ? 0 : 1; }
         if (any_resample) {
             dim3 grid((p->img_h + HROWS - 1) / HROWS, nf);
+            Prof prof(KC_PYR_H, st, 0, (double)nf * n_res * (double)frame_bytes, 0.0);
             pyr_hpass_kernel<<<grid, 256, smem, st>>>(fr, p->img_h, p->img_w, p->d_hitems, p->n_hitems,
                                                        reinterpret_cast<const uint4*>(p->d_hcoef), sc, p->scratch_bytes);
             RODC_LAUNCH_CHECK();
         }
         dim3 grid(p->total_rows, nf);
+        Prof prof(KC_PYR_V, st, 0, (double)nf * lv_bytes, 0.0);
         pyr_vpass_kernel<<<grid, 128, 0, st>>>(fr, p->img_h, p->img_w, p->d_levels, nl, p->d_tables, p->d_row_start,
                                                 sc, p->scratch_bytes, py, p->pyramid_bytes);
         RODC_LAUNCH_CHECK();
@@ -233,6 +239,7 @@ extern "C" int rodc_extract_windows(rodc_plan* p, const uint8_t* pyramid, int n_
     int rc = p->ensure_device(); if (rc) return rc;
     const int64_t rows = N * n_frames * p->win;
     int blocks = (int)((rows + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+    Prof prof(KC_SOURCE, as_stream(stream), p->win, 2.0 * (double)N * n_frames * p->win * p->win * 3, 0.0);
     extract_windows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pyramid, p->pyramid_bytes, p->d_levels, p->d_win, N, p->win, rows, windows);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
@@ -245,6 +252,7 @@ extern "C" int rodc_window_meta(rodc_plan* p, int n_frames, int frame_id_base, i
     int rc = p->ensure_device(); if (rc) return rc;
     const int64_t total = N * n_frames;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof(KC_WINTAB, as_stream(stream), 0, 52.0 * (double)total, 0.0);
     window_meta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, N, total, frame_id_base, meta);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
@@ -259,6 +267,7 @@ extern "C" int rodc_window_gather_rows(rodc_plan* p, int n_frames, int64_t pyram
     int rc = p->ensure_device(); if (rc) return rc;
     const int64_t total = N * n_frames;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof(KC_WINTAB, as_stream(stream), 0, 44.0 * (double)total, 0.0);
     window_gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, p->d_levels, N, total, pyramid_base_off,
                                                                      p->pyramid_bytes, win_off, win_pitch);
     RODC_LAUNCH_CHECK();
@@ -272,6 +281,7 @@ extern "C" int rodc_window_levels(rodc_plan* p, int n_frames, int slot_base, int
     int rc = p->ensure_device(); if (rc) return rc;
     const int64_t total = N * n_frames;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof(KC_WINTAB, as_stream(stream), 0, 36.0 * (double)total, 0.0);
     window_levels_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p->d_win, N, total, slot_base, out);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
@@ -283,6 +293,7 @@ extern "C" int rodc_select_rows(const void* in, const int32_t* idx, int64_t n, i
     if (n <= 0) return RODC_OK;
     const int64_t total = n * (row_bytes / 4);
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof(KC_MISC, as_stream(stream), 0, (double)n * (2.0 * row_bytes + 4.0), 0.0);
     select_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(in), idx, n, row_bytes / 4,
                                                               static_cast<uint32_t*>(out));
     RODC_LAUNCH_CHECK();
@@ -296,6 +307,7 @@ extern "C" int rodc_window_scaled_rows(const int32_t* meta, const int32_t* slot,
     RODC_CHECK_ARG(size > 0 && n_slots > 0, "rodc_window_scaled_rows: bad size %d / %d slots", size, n_slots);
     if (n <= 0) return RODC_OK;
     int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof(KC_MISC, as_stream(stream), 0, (double)n * 36.0, 0.0);
     window_scaled_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(meta, slot, n, slots, n_slots, size, dense_rel_off,
                                                                      win_off, win_pitch, err);
     RODC_LAUNCH_CHECK();

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
 
 int prepare_fc1_split(rodc_stage* s, cudaStream_t st) {
     dim3 grid((unsigned)((s->K + 31) / 32), (unsigned)((s->fc1_size + 31) / 32));
+    Prof prof(KC_MISC, st, 0, 8.0 * (double)s->K * s->fc1_size, 0.0);
     split_transpose_kernel<<<grid, 256, 0, st>>>(s->fc1_w, s->K, s->fc1_size, ldexpf(1.f, s->w_exp), s->fc1_hi, s->fc1_lo);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
@@ -65,62 +66,9 @@ static int pow2_headroom(double bound, double limit) {
     return e;
 }
 
-// ---- measurement hook (off by default)
-struct ProfRec { cudaEvent_t a, b; double flops; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
-static cudaEvent_t g_prof_pending = nullptr;
-
-void profile_begin(cudaStream_t st) {
-    if (!g_prof_on) return;
-    cudaEvent_t a;
-    if (cudaEventCreate(&a) != cudaSuccess) return;
-    cudaEventRecord(a, st);
-    g_prof_pending = a;
-}
-
-void profile_end(cudaStream_t st, double flops) {
-    if (!g_prof_on || !g_prof_pending) return;
-    cudaEvent_t b;
-    if (cudaEventCreate(&b) != cudaSuccess) return;
-    cudaEventRecord(b, st);
-    g_prof.push_back({g_prof_pending, b, flops});
-    g_prof_pending = nullptr;
-}
-
 }  // namespace rodc
 
 using namespace rodc;
-
-extern "C" int rodc_profile_enable(int on) {
-    g_prof_on = on != 0;
-    return RODC_OK;
-}
-
-extern "C" int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* fc1_launches,
-                                    double* dom_ms, double* dom_flops, int64_t* dom_launches) {
-    double ms = 0.0, fl = 0.0, dms = 0.0, dfl = 0.0, maxfl = 0.0;
-    int64_t dn = 0;
-    std::vector<float> t(g_prof.size(), 0.f);
-    for (size_t i = 0; i < g_prof.size(); ++i) {
-        ProfRec& r = g_prof[i];
-        RODC_CUDA(cudaEventSynchronize(r.b));
-        RODC_CUDA(cudaEventElapsedTime(&t[i], r.a, r.b));
-        ms += t[i]; fl += r.flops;
-        if (r.flops > maxfl) maxfl = r.flops;
-        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
-    }
-    for (size_t i = 0; i < g_prof.size(); ++i)
-        if (g_prof[i].flops == maxfl) { dms += t[i]; dfl += g_prof[i].flops; ++dn; }
-    if (fc1_ms) *fc1_ms = ms;
-    if (fc1_flops) *fc1_flops = fl;
-    if (fc1_launches) *fc1_launches = (int64_t)g_prof.size();
-    if (dom_ms) *dom_ms = dms;
-    if (dom_flops) *dom_flops = dfl;
-    if (dom_launches) *dom_launches = dn;
-    g_prof.clear();
-    return RODC_OK;
-}
 
 extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, int n_prev,
                                  const float* conv_w, const float* conv_b,
@@ -346,16 +294,12 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         if (impl == RODC_IMPL_SIMT) {
             float* feat = reinterpret_cast<float*>(workspace);
             if ((rc = launch_features(s, csrc, cfirst, m, feat, nullptr, nullptr, st, gscratch))) return rc;
-            profile_begin(st);
             if ((rc = launch_fc1_simt(s, feat, m, bott, ld_bott, st))) return rc;
-            profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         } else {
             __half* hi = reinterpret_cast<__half*>(workspace);
             __half* lo = hi + m * s->K;
             if ((rc = launch_features(s, csrc, cfirst, m, nullptr, hi, lo, st, gscratch))) return rc;
-            profile_begin(st);
             if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
-            profile_end(st, 2.0 * (double)m * (double)s->K * (double)s->fc1_size);
         }
     }
     return launch_fc2_softmax(s, bottleneck, ld_bott, n, logits, probs, st);

@@ -59,8 +59,5 @@ int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int6
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
                       float* bott, int ld_bott, cudaStream_t st);
 int prepare_fc1_split(rodc_stage* s, cudaStream_t st);
-// stage.cu: measurement hook around the fc1 launches
-void profile_begin(cudaStream_t st);
-void profile_end(cudaStream_t st, double flops);
 
 }  // namespace rodc

@@ -13,11 +13,19 @@ import numpy as np
 class ArrayImageInfo:
     """An in-memory ``[H,W,3]`` uint8 frame (synthetic frames, video streams)."""
 
-    def __init__(self, array: np.ndarray, key: str, dataset_key: str = "memory"):
+    def __init__(self, array: np.ndarray, key: str, dataset_key: str = "memory", pin: bool = False):
+        """``pin=True`` keeps the frame in page-locked host memory (``cudaHostAlloc`` through torch), from where the
+        engine uploads it with one asynchronous copy and no staging pass."""
         a = np.asarray(array)
         if a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8:
             raise ValueError("expected an [H,W,3] uint8 array")
-        self._array = np.ascontiguousarray(a)
+        if pin:
+            import torch
+            self._pinned = torch.empty(a.shape, dtype=torch.uint8).pin_memory()
+            self._array = self._pinned.numpy()
+            self._array[...] = a
+        else:
+            self._array = np.ascontiguousarray(a)
         self._key = key
         self._dataset_key = dataset_key
 

@@ -63,9 +63,26 @@ class CascadeEngine:
         self._plans: Dict[Tuple, native.Plan] = {}
         self._scaled_plans: Dict[Tuple, native.Plan] = {}
         self._ws: Optional[torch.Tensor] = None
-        self.kernel_launches = 0        # launches of OUR kernels (bench.py reports it)
+        self._validate_chain()
 
     # ------------------------------------------------------------------ helpers
+    def _validate_chain(self):
+        """The bottleneck hand-off trusts nothing: stage i + 1 concatenates ``[own fc1 | previous bottleneck]``
+        (`network/net.py:140-145`), so its fc2 must have exactly ``width(stage i)`` extra rows and stage 0 none
+        (TensorFlow would refuse to feed a placeholder of another shape, `app/inference_cascade_app.py:203-215`)."""
+        st = self.stages
+        if st[0].n_prev != 0:
+            raise ValueError("stage 0 expects a previous bottleneck of %d values, but a cascade starts without one" % st[0].n_prev)
+        for i in range(len(st) - 1):
+            if st[i + 1].n_prev not in (0, st[i].width):
+                raise ValueError("stage %d expects a previous bottleneck of %d values, stage %d provides %d"
+                                 % (i + 1, st[i + 1].n_prev, i, st[i].width))
+
+    @property
+    def kernel_launches(self) -> int:
+        """Kernel launches issued by librodc in this process so far (measured inside the library)."""
+        return int(native._lib.lib().rodc_launch_count())
+
     def plan_for(self, w: int, h: int) -> native.Plan:
         key = (w, h, self.sizes[0], float(cf.get("window_scale_factor")), float(cf.get("min_window_length")))
         p = self._plans.get(key)
@@ -127,7 +144,6 @@ class CascadeEngine:
             pos = {k: j for j, k in enumerate(sel)}
             if plan2 is not None:
                 native.pyramid(plan2, fr, out=buf[base:base + nf * plan2.pyramid_bytes].view(nf, plan2.pyramid_bytes))
-                self.kernel_launches += 2
             for k in range(len(ns)):
                 if k in pos:
                     j = pos[k]
@@ -140,9 +156,7 @@ class CascadeEngine:
         if any_individual:                    # mixed: those survivors keep the crop + cv2.resize input (K4, materialised)
             dense = native.recrop(table, meta[:n], size)
             rel = dense.data_ptr() - buf.data_ptr()
-            self.kernel_launches += 1
         win_off, win_pitch, err = native.window_scaled_rows(meta, slot, n, slots, len(entries), size, rel)
-        self.kernel_launches += 1
         flags = int(err.item())
         if flags & 1:
             raise ValueError("ymax/xmax must not leave the image boundaries")      # `data/rectangles.py:286-289`
@@ -169,15 +183,6 @@ class CascadeEngine:
     @staticmethod
     def _impl() -> int:
         return native.IMPL_SIMT if cf.get("fc1_impl") == cf.FC1_IMPL_SIMT else native.IMPL_TENSOR
-
-    def _count_stage_launches(self, stage: native.Stage, n: int, ws_bytes: int, dense: bool):
-        """Launches of one ``rodc_stage_forward``: per chunk (window copy unless the source is dense) + features +
-        fc1, then one fc2/softmax."""
-        win = (stage.in_size * stage.in_size * 3 + 15) // 16 * 16
-        chunk = max(1, ws_bytes // (stage.K * 4 + win))
-        if chunk >= 128:
-            chunk = chunk // 128 * 128
-        self.kernel_launches += (2 if dense else 3) * ((n + chunk - 1) // chunk) + 1
 
     # ------------------------------------------------------------------ stages on a window set
     def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
@@ -209,21 +214,24 @@ class CascadeEngine:
             if keep_trace:                      # the stage's u8 input, i.e. the reference's windows_raw (tests)
                 trace["X"].append(native.source_windows(src, 0, n, st.in_size, dev))
             logits, probs = native.stage_forward(st, src, 0, n, bott, ws[:ws_bytes], impl)
-            self._count_stage_launches(st, n, ws_bytes, dense=src.kind == native.SRC_DENSE)
-            # single net: keep argmax != background <=> p[1] > p[0] <=> p[1] > 0.5 (ties -> background,
-            # np.argmax picks index 0), confidence = p[argmax] = p[1]   (inference_app.py:140-149)
-            thr = 0.5 if self.single else self._threshold(i)
+            # single net: keep argmax != background <=> p[1] > p[0] (ties -> background, np.argmax picks index 0),
+            # confidence = p[argmax] = p[1] (inference_app.py:140-149); NaN selects that rule in rodc_compact
+            thr = float("nan") if self.single else self._threshold(i)
             meta_out = torch.empty((n, 5), dtype=torch.int32, device=dev)
             conf_out = torch.empty((n,), dtype=torch.float32, device=dev)
             use_b = (not last) and bool(cf.get("reuse_bottlenecks"))
             nxt = self.stages[i + 1] if not last else None
+            if nxt is not None and nxt.n_prev > 0 and not use_b:
+                # the reference would leave the bottleneck_in placeholder unfed and TensorFlow raises
+                # (`app/inference_cascade_app.py:203-215`); never run fc2 over uninitialised columns
+                raise ValueError("stage %d was built with a %d-wide bottleneck input but reuse_bottlenecks is off"
+                                 % (i + 1, nxt.n_prev))
             bott_next = torch.empty((n, nxt.width), dtype=torch.float32, device=dev) if nxt is not None else None
             keep, count = native.compact(
                 probs, n, thr, meta_in=meta, meta_out=meta_out,
                 bott_in=bott if use_b and nxt.n_prev > 0 else None, width=st.width,
                 bott_out=bott_next if use_b and nxt.n_prev > 0 else None, col_off=nxt.fc1_size if nxt is not None else 0,
                 conf_acc=conf_acc, conf_out=conf_out, conf_mode=conf_mode if conf_acc is not None else native.CONF_LAST)
-            self.kernel_launches += 4 if (use_b and nxt.n_prev > 0) else 3
             kept = int(count.item())                                        # one host sync per stage
             res.stage_in.append(n); res.stage_kept.append(kept)
             if keep_trace:
@@ -237,11 +245,9 @@ class CascadeEngine:
                     # the reference appends windows_raw[window_index_original] only next to the bottleneck copy
                     # (`:234-237`); without reuse_bottlenecks it would feed an empty array -- the windows are kept here too
                     rows = (rows[0], native.select_rows(rows[1], keep, kept), native.select_rows(rows[2], keep, kept))
-                    self.kernel_launches += 2
                     src = native.make_source(gather_base=rows[0], win_off=rows[1], win_pitch=rows[2])
                 elif scaled:
                     slot = native.select_rows(slot, keep, kept)
-                    self.kernel_launches += 1
                     src = self._scaled_source(origin, nxt.in_size, meta, slot, kept, table)
                 if src is None:
                     src = native.make_source(table=table, meta=meta)
@@ -264,7 +270,6 @@ class CascadeEngine:
             return res
         if cf.get("nms") == cf.NMS_OPENCV:
             out, count = native.group_rectangles(meta, k, n_frames, int(cf.get("nms_opencv_min_neighbors")), 0.2)
-            self.kernel_launches += 6
             kk = int(count.item())
             rows = out[:kk].cpu().numpy()
             res.frame = rows[:, 0].copy()
@@ -312,6 +317,16 @@ class CascadeEngine:
         n = len(frames)
         h, w, _ = frames[0].shape
         need = n * h * w * 3
+        # frames that already live in page-locked memory (``ArrayImageInfo(..., pin=True)``, capture buffers) are
+        # copied straight from where they are: n asynchronous H2D copies, no host-side gather
+        tens = [torch.from_numpy(f) if f.flags["C_CONTIGUOUS"] and f.flags["WRITEABLE"] else None for f in frames]
+        if all(t is not None and t.is_pinned() for t in tens):
+            with torch.cuda.device(self.device):
+                dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+                for i, t in enumerate(tens):
+                    dev[i].copy_(t, non_blocking=True)
+            self._keepalive_host = tens
+            return dev
         buf = getattr(self, "_pinned", None)
         if buf is None or buf.numel() < need:
             buf = torch.empty((need,), dtype=torch.uint8).pin_memory()
@@ -355,9 +370,7 @@ class CascadeEngine:
             if not plan.fits:
                 raise ValueError("xmax/ymax must not leave the image boundaries")           # rectangles.py:286-289
             pyr = native.pyramid(plan, frames)
-            self.kernel_launches += 2
             meta0 = native.window_meta(plan, n, 0, self.device)
-            self.kernel_launches += 1
             table = native.FrameTable.from_batch(frames)
             src0 = native.make_source(plan=plan, pyr=pyr)
             origin = None
@@ -366,13 +379,11 @@ class CascadeEngine:
                     off = torch.empty((n * plan.n_windows,), dtype=torch.int64, device=self.device)
                     pitch = torch.empty((n * plan.n_windows,), dtype=torch.int32, device=self.device)
                     native.window_gather_rows(plan, n, 0, off, pitch)
-                    self.kernel_launches += 1
                     return pyr, off, pitch
                 origin = WindowOrigin(gather=_rows)
             elif len(self.stages) > 1 and self._scaled_branch_possible():
                 origin = WindowOrigin(slot=native.window_levels(plan, n, 0, self.device),
                                       groups=[dict(frames=frames, frame_base=0, scales=plan.scale, width=plan.win)])
-                self.kernel_launches += 1
             return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, origin)
 
     def run_mixed(self, frames: Sequence[np.ndarray], keep_trace: bool = False) -> Tuple[GroupResult, List[int]]:
@@ -426,10 +437,8 @@ class CascadeEngine:
                 nw = n * p.n_windows
                 native.window_gather_rows(p, n, pbase, win_off[wbase:wbase + nw], win_pitch[wbase:wbase + nw])
                 native.window_meta(p, n, fbase, self.device, out=meta0[wbase:wbase + nw])
-                self.kernel_launches += 4
                 if want_slots:
                     native.window_levels(p, n, sbase, self.device, out=slot0[wbase:wbase + nw])
-                    self.kernel_launches += 1
                     slot_groups.append(dict(frames=d, frame_base=fbase, scales=p.scale, width=p.win))
                     sbase += p.n_levels
                 fbase += n; wbase += nw; pbase += n * p.pyramid_bytes; pos += n
