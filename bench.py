@@ -1,23 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the cascade-inference hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--frames B] [--impl ours|reference]
 
-A "step" is one pass of the whole path (pyramid -> 3 cascade stages with compaction and fused
-re-crop -> groupRectangles) over one batch of B (default 32) synthetic 640x480 frames with random-init
-(Xavier) weights of the reference architecture: BASELINE config 2, batched.  Prints ONE JSON line.
+A "step" is one pass of the whole path (pyramid -> 3 cascade stages with compaction and re-crop ->
+groupRectangles) over one batch of synthetic frames with random-init (Xavier) weights of the reference
+architecture.  `--config` picks the BASELINE.json configuration (default 2, the one the metric is quoted on):
+
+  2  B (default 32) 640x480 frames per GPU and step, full pyramid, uncalibrated weights (87 / 100 / 79 % pass
+     rates: the heavy case)                                                                   weak scaling
+  3  FDDB-shaped batch: `--frames` (default 2845) frames of 35 shapes around 450x400, frame j on rank
+     j mod world_size, all shapes merged into one launch set per chunk                        STRONG scaling
+  4  1920x1080 stream, window_scale_factor 1.2, min window 24 px: 93 645 windows / frame      weak scaling
+  5  3840x2160, min_window_length 0.0125: 161 969 windows / frame, > 99.9 % stage-1 rejection weak scaling
+Configs 3-5 add the documented fc2.b[1] offsets for realistic pass rates.  Prints ONE JSON line.
 
   value      frames/s with the frame batch already resident in HBM (device-timed, CUDA events)
-  e2e        the same metric through the public API (InferenceCascadeApp.run_inference_on_images)
-             with HOST frames: pinned H2D copy and D2H of the boxes inside the timed region
+  e2e        the same metric through the public API (dist.run_sharded -> InferenceCascadeApp.run_inference_on_images)
+             with HOST frames in pinned memory: H2D copies, the D2H of the boxes and the NCCL gather inside
   roofline   the dominant kernel (tcgen05 split-fp16 fc1), timed live with CUDA events on its stream
+  kernels    per kernel class: ms per step, algorithmic bytes / FLOPs, bound, fraction of peak
+             (measured by the library in two extra steps after the timed region)
   cpu_baseline  the oracle port (oracle/cascade.py: per-window Python extraction + Pillow + cv2 +
-             torch-CPU fp32 stage nets) on the host cores, bounded sample
+             torch-CPU fp32 stage nets) on the host cores, bounded sample of the same workload
 
 `--impl reference` times that CPU port alone (TensorFlow 1.4, the reference's own runtime, cannot
 be installed: no wheel for py3.12, no network) on rank 0 and prints the line with "impl": "reference".
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -33,26 +44,48 @@ if REPO not in sys.path:
 
 METRIC = "cascade frames/sec at 640x480 full pyramid"
 UNIT = "frames/s"
-FRAME_H, FRAME_W = 480, 640
-WINDOWS_PER_FRAME = 5061
 FLOPS_PER_WINDOW = [4969472, 19873792, 79484928]       # SURVEY.md §8a (2*MAC), stages 0/1/2
-NCU_FC1_TRAFFIC_BYTES = 5925631000 + 26252288          # dram__bytes_read.sum + dram__bytes_write.sum of one m = 18944 launch
-                                                       # of the pair kernel (profiles/r1h_ncu_full_fc1_pair.txt)
+
+CONFIGS = {
+    2: dict(shape=(480, 640), frames=32, cf={}, offsets=None, seed=0, scaling="weak", windows=5061,
+            text="BASELINE config 2 batched: %d synthetic 640x480 frames per GPU and step, full pyramid (factor 1.1, "
+                 "min_window_length 0.075, 24 levels, 5061 windows/frame), 3-stage 12/24/48 cascade with bottleneck reuse, "
+                 "Xavier random-init weights (uncalibrated: 87/100/79 %% pass rates), thresholds 0.5, groupRectangles(min_neighbors=1)"),
+    3: dict(shape=None, frames=2845, cf={}, offsets=[-40.0, -85.0, -24.0], seed=100, scaling="strong", windows=6461,
+            text="BASELINE config 3: %d synthetic FDDB-shaped frames (W = 450 - 10 (j mod 5), H = 400 - 8 (j mod 7), 35 shapes, "
+                 "seeds 100 + j) per step in total, frame j on rank j mod world_size, all shapes merged into one launch set per "
+                 "chunk, Xavier weights + fc2.b[1] offsets [-40, -85, -24], thresholds 0.5, groupRectangles"),
+    4: dict(shape=(1080, 1920), frames=32, cf={"window_scale_factor": 1.2, "min_window_length": 0.0125},
+            offsets=[-60.0, -85.0, -24.0], seed=5000, scaling="weak", windows=93645,
+            text="BASELINE config 4: %d synthetic 1920x1080 frames per GPU and step (BASELINE: 256), window_scale_factor 1.2, "
+                 "min window 24 px (min_window_length 0.0125): 21 levels, 93 645 windows/frame, Xavier weights + offsets "
+                 "[-60, -85, -24], cascade + groupRectangles"),
+    5: dict(shape=(2160, 3840), frames=8, cf={"min_window_length": 0.0125}, offsets=[None, -85.0, -24.0], seed=9000,
+            scaling="weak", windows=161969,
+            text="BASELINE config 5: %d synthetic 3840x2160 frames per GPU and step (BASELINE: 32), factor 1.1, min_window_length "
+                 "0.0125: 40 levels, 161 969 windows/frame, stage-1 offset self-calibrated for > 99.9 %% rejection, offsets "
+                 "[auto, -85, -24], cascade + groupRectangles"),
+}
 
 
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), float(d.get("bf16_tflops", 0.0)) or None, "measured"
+    return 1400.0, 6650.0, None, "fallback (B200_PROFILING.md)"
 
 
-def measured_burst_peak():
-    """cuBLAS bf16 best-of-10 TFLOP/s (a kernel timed alone), None without MEASURED_PEAKS.json."""
-    p = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return float(json.load(open(p)).get("bf16_tflops", 0.0)) or None
+def ncu_traffic(kernel: str, shape: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed `ncu --set full` capture of the same
+    kernel and launch shape (profiles/ncu_traffic.json, written from the .ncu-rep files of this round), else None."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    try:
+        for row in json.load(open(p)):
+            if row["kernel"] == kernel and row["shape"] == shape:
+                return row
+    except (OSError, ValueError, KeyError):
+        pass
     return None
 
 
@@ -101,20 +134,53 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_time(n_frames_max: int, budget_s: float):
+# ----------------------------------------------------------------------------- workloads
+def frame_spec(cfg_id: int, j: int):
+    """(H, W, seed) of global frame j of a configuration."""
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    c = CONFIGS[cfg_id]
+    if cfg_id == 3:
+        h, w = synth.fddb_shape(j)
+        return h, w, c["seed"] + j
+    return c["shape"][0], c["shape"][1], c["seed"] + j
+
+
+def my_frame_ids(cfg_id: int, n_frames: int, rank: int, world: int):
+    """Global ids of this rank's frames.  Weak scaling: n_frames per rank, ids interleaved so that run_sharded's
+    j mod world_size rule hands every rank exactly its own; strong scaling: n_frames in total."""
+    total = n_frames if CONFIGS[cfg_id]["scaling"] == "strong" else n_frames * world
+    return list(range(rank, total, world)), total
+
+
+def cascade_weights(cfg_id: int, offset0=None):
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    offs = CONFIGS[cfg_id]["offsets"]
+    if offs is None:
+        return synth.xavier_cascade()
+    offs = [offset0 if o is None else o for o in offs]
+    return synth.xavier_cascade(fg_bias_offsets=offs)
+
+
+# ----------------------------------------------------------------------------- CPU port
+def cpu_port_time(cfg_id: int, n_frames_max: int, budget_s: float, offset0=None):
     """Oracle port on the host cores: whole path per frame.  Returns (frames/s, frames timed, cores)."""
     import torch
     from oracle import cascade as oc
     from rapidobjectdetectionusingcascadedcnns_b200 import synth
     cores = os.cpu_count() or 1
+    if hasattr(os, "sched_getaffinity"):
+        cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    weights = synth.xavier_cascade()
-    cfg = oc.Config()
+    if cfg_id == 5 and offset0 is None:
+        offset0 = -120.0            # without a GPU to self-calibrate: a stage-1 offset that rejects > 99.9 % as well
+    weights = cascade_weights(cfg_id, offset0)
+    cfg = oc.Config(**CONFIGS[cfg_id]["cf"])
     # untimed warm-up (thread pool, allocator, lazy imports) on a small frame
     oc.run_cascade([synth.synth_frame(96, 128, 99)], weights, oc.Config(min_window_length=0.2), dtype=torch.float32, arith="lib")
     done, t_total = 0, 0.0
     for j in range(n_frames_max):
-        fr = synth.synth_frame(FRAME_H, FRAME_W, j)
+        h, w, seed = frame_spec(cfg_id, j)
+        fr = synth.synth_frame(h, w, seed)
         t0 = time.perf_counter()
         oc.run_cascade([fr], weights, cfg, dtype=torch.float32, arith="lib")
         t_total += time.perf_counter() - t0
@@ -128,33 +194,36 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    fps, done, cores = cpu_port_time(steps + min(args.warmup, 1), budget_s=150.0)
+    fps, done, cores = cpu_port_time(args.config, steps + min(args.warmup, 1), budget_s=150.0)
+    c = CONFIGS[args.config]
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-            "warmup": 0, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
+            "warmup": 0, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": c["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: 640x480 synthetic frame, full pyramid (factor 1.1, "
-                                   "min_window_length 0.075, 5061 windows), 3-stage 12/24/48 cascade, Xavier weights, "
-                                   "thresholds 0.5, groupRectangles; one frame per step"},
+            "config": {"workload": (c["text"] % 1) + "; CPU port: one frame per step", "config_id": args.config},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d frame(s), whole path, torch-CPU fp32 + Pillow + cv2 (TensorFlow 1.4 not installable)" % done},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=32, help="frames per step and per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step: per GPU (configs 2/4/5) or in total (config 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fc1", default="tensor", choices=["tensor", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -168,36 +237,72 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    cores = rdist.bind_rank_to_cores(local_rank, local_world)        # each rank (and its copy pool) on its own cores
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
-    B = args.frames
+    cid = args.config
+    conf = CONFIGS[cid]
+    B = args.frames or conf["frames"]
     pkg.cf.reset()
     pkg.cf.set("fc1_impl", args.fc1)
+    for k, v in conf["cf"].items():
+        pkg.cf.set(k, v)
+    if cid in (4, 5):
+        pkg.cf.set("max_windows_per_launch", 1 << 22)       # 2.2 KB of stage-0 state per window: 9 GB of the 180 GB
 
-    # this rank's frames (weak scaling: B frames per GPU and step; seeds differ per rank)
-    host_frames = [synth.synth_frame(FRAME_H, FRAME_W, rank * B + j) for j in range(B)]
-    weights = synth.xavier_cascade()
+    ids, total_frames = my_frame_ids(cid, B, rank, world)
+    host_frames = [synth.synth_frame(*frame_spec(cid, j)) for j in ids]
+    # config 5: stage-1 offset for > 99.9 % rejection from the margins of the uncalibrated stage 0 on this rank's first frames
+    offset0 = None
+    if cid == 5:
+        pkg.cf.set("foreground_confidence_threshold", [2.0, 0.5, 0.5])
+        probe = CascadeEngine(synth.xavier_cascade(), device=local_rank)
+        lg = probe.run_frames(np.stack(host_frames[:2]), keep_trace=True).trace["logits"][0].cpu().numpy()
+        del probe
+        pkg.cf.set("foreground_confidence_threshold", 0.5)
+        offset0 = -round(float(np.quantile(lg[:, 1] - lg[:, 0], 1 - 0.0005)) * 64) / 64
+        if world > 1:                                       # one offset for the whole job: rank 0's
+            t = torch.tensor([offset0], dtype=torch.float64, device=dev)
+            dist.broadcast(t, 0)
+            offset0 = float(t.item())
+    weights = cascade_weights(cid, offset0)
     models = [pkg.StageModel(w) for w in weights]
     app = pkg.InferenceCascadeApp("bench", stage_models=models, device=local_rank)
     app._init_tf()
     eng: CascadeEngine = app._engine
-    infos = [pkg.ArrayImageInfo(f, "bench_r%d_%d.png" % (rank, j)) for j, f in enumerate(host_frames)]
-    d_frames = torch.from_numpy(np.stack(host_frames)).to(dev)
+    # e2e inputs: this rank's frames in PINNED host memory inside the global image list (other ranks' slots stay empty)
+    infos = [None] * total_frames
+    for j, f in zip(ids, host_frames):
+        infos[j] = pkg.ArrayImageInfo(f, "bench_%d.png" % j, pin=True)
+    h2d_bytes = int(sum(f.size for f in host_frames))
+
+    # resident inputs, cut like the app cuts them (cf max_windows_per_launch)
+    budget = int(pkg.cf.get("max_windows_per_launch"))
+    chunks, cur, acc = [], [], 0
+    for f in host_frames:
+        nw = eng.plan_for(f.shape[1], f.shape[0]).n_windows
+        if cur and acc + nw > budget:
+            chunks.append(cur); cur, acc = [], 0
+        cur.append(f); acc += nw
+    if cur:
+        chunks.append(cur)
+    if cid == 3:
+        resident = [eng.upload_mixed(c) for c in chunks]
+        run_chunk = eng.run_mixed_device
+    else:
+        resident = [torch.from_numpy(np.stack(c)).to(dev) for c in chunks]
+        run_chunk = eng.run_frames
+    torch.cuda.synchronize()
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def gather(res):
-        if world > 1:
-            rows = np.column_stack([res.frame + rank * B, res.boxes, res.conf]).astype(np.float64).reshape(-1, 6)
-            rdist.gather_detections(rows, dev)
 
     def timed(fn, steps):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed (untimed) in between."""
@@ -219,29 +324,36 @@ def main():
     last = {}
 
     def step_resident():
-        res = eng.run_frames(d_frames)
-        gather(res)
-        last["res"] = res
+        rows, fbase, kept, n_in = [], 0, None, None
+        for d, c in zip(resident, chunks):
+            res = run_chunk(d)
+            gid = np.asarray(ids[fbase:fbase + len(c)], np.float64)
+            if cid == 3:                                     # internal ids are grouped by shape
+                gid = gid[np.asarray(d.order)]
+            rows.append(np.column_stack([gid[res.frame], res.boxes, res.conf]).astype(np.float64).reshape(-1, 6))
+            fbase += len(c)
+            kept = res.stage_kept if kept is None else [a + b for a, b in zip(kept, res.stage_kept)]
+            n_in = res.stage_in if n_in is None else [a + b for a, b in zip(n_in, res.stage_in)]
+        allrows = rdist.gather_detections(np.concatenate(rows), dev)       # the one collective (N > 1)
+        last["rows"], last["kept"], last["in"] = allrows, kept, n_in
 
     def step_e2e():
-        out = app.run_inference_on_images(infos, merge=True)
-        last["out"] = out
+        last["e2e_rows"] = rdist.run_sharded(app, infos, merge=True, as_rows=True)
 
+    L = _lib.lib()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                                    # started early: nvidia-smi takes a while to come up
     for _ in range(warmup):
         step_resident()
     barrier()
-    L = _lib.lib()
     L.rodc_profile_enable(1)
-    eng.kernel_launches = 0
+    launches0 = int(L.rodc_launch_count())
     t_begin = time.time()
     ms_total = timed(step_resident, args.steps)
     t_end = time.time()
+    launches = int(L.rodc_launch_count()) - launches0
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    launches = eng.kernel_launches
-    import ctypes as C
     fc1_ms, fc1_fl, fc1_n = C.c_double(), C.c_double(), C.c_int64()
     dom_ms, dom_fl, dom_n = C.c_double(), C.c_double(), C.c_int64()
     L.rodc_profile_collect(C.byref(fc1_ms), C.byref(fc1_fl), C.byref(fc1_n), C.byref(dom_ms), C.byref(dom_fl), C.byref(dom_n))
@@ -251,69 +363,121 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # per-kernel table: two more steps with every kernel class bracketed by events (not part of `value`)
+    ktable, k_steps = [], 2
+    if not args.no_kernel_table:
+        L.rodc_profile_enable(2)
+        ms_k = timed(step_resident, k_steps)
+        L.rodc_profile_collect(None, None, None, None, None, None)
+        L.rodc_profile_enable(0)
+        n = 64
+        kc, sub = (C.c_int32 * n)(), (C.c_int32 * n)()
+        kms, kby, kfl = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        kln, krec = (C.c_int64 * n)(), (C.c_int64 * n)()
+        rows = L.rodc_profile_table(n, kc, sub, kms, kby, kfl, kln, krec)
+        for i in range(rows):
+            ktable.append(dict(kc=int(kc[i]), name=L.rodc_kernel_class_name(int(kc[i])).decode(), side=int(sub[i]), ms=float(kms[i]),
+                               bytes=float(kby[i]), flops=float(kfl[i]), launches=int(kln[i])))
+        ktable_step_ms = ms_k / k_steps
+
     # BASELINE config 2 literally (ONE 640x480 frame per call): latency-bound, reported beside the batched value
-    one = d_frames[:1].contiguous()
-    for _ in range(3):
-        eng.run_frames(one)
-    ms_one = timed(lambda: eng.run_frames(one), 5) / 5.0
+    single = None
+    if cid == 2:
+        one = resident[0][:1].contiguous()
+        for _ in range(3):
+            eng.run_frames(one)
+        ms_one = timed(lambda: eng.run_frames(one), 10) / 10.0
+        single = {"ms_per_frame": ms_one, "frames_per_s": 1000.0 / ms_one,
+                  "note": "one 640x480 frame per call (no batching): 5061 windows fill < 1 wave of 148 SMs"}
 
     if rank == 0:
-        res = last["res"]
-        frames_total = B * world * args.steps
-        value = frames_total / (ms_total / 1000.0)
-        e2e = frames_total / (ms_e2e / 1000.0)
-        peak_tf, peak_hbm, which = measured_peaks()
-        peak_burst = measured_burst_peak()
+        frames_step = total_frames if conf["scaling"] == "strong" else B * world
+        value = frames_step * args.steps / (ms_total / 1000.0)
+        e2e = frames_step * args.steps / (ms_e2e / 1000.0)
+        peak_tf, peak_hbm, peak_burst, which = measured_peaks()
         mma_per_product = 3 if args.fc1 == "tensor" else 1
-        # roofline of the dominant kernel on its dominant shape (full stage-2 chunks, K = 73728)
+        # roofline of the dominant kernel on its dominant shape (the largest fc1 launches of the step)
         achieved = dom_fl.value / (dom_ms.value / 1000.0) / 1e12 if dom_ms.value > 0 else 0.0
         achieved_all = fc1_fl.value / (fc1_ms.value / 1000.0) / 1e12 if fc1_ms.value > 0 else 0.0
-        dom_windows = dom_fl.value / max(dom_n.value, 1) / (2.0 * 73728 * 512)
-        peak = peak_tf / 3.0
-        n_boxes = int(sum(len(p) for p in last["out"]))
-        d2h = int(res.boxes.shape[0]) * 6 * 4 + 8 * (len(res.stage_kept) + 1)
+        dom_launch_fl = dom_fl.value / max(dom_n.value, 1)
+        kd = 73728 if dom_launch_fl >= 2.0 * 73728 * 512 * 128 else (18432 if dom_launch_fl >= 2.0 * 18432 * 512 * 128 else 4608)
+        if cid != 2:                                        # the dominant launch may belong to any stage: find K from the table
+            for K in (73728, 18432, 4608):
+                m = dom_launch_fl / (2.0 * K * 512)
+                if abs(m - round(m)) < 1e-6 and m >= 1:
+                    kd = K
+                    break
+        dom_windows = dom_launch_fl / (2.0 * kd * 512)
+        peak = peak_tf / 3.0 if args.fc1 == "tensor" else None
+        kernel_name = "rodc::tc::fc1_tc2_kernel<256,3> (cta_group::2 pairs)" if args.fc1 == "tensor" else "rodc::fc1_simt_kernel"
+        shape = "m=%d windows x K=%d x N=512" % (int(round(dom_windows)), kd)
+        tr = ncu_traffic(kernel_name.split(" ")[0], shape)
+        # K2's algorithmic bytes are the u8 window in and the bottleneck row out (weights L2 resident);
+        # the A planes the un-fused pipeline materialises are DESIGN traffic, reported separately so the ratio shows
+        alg_bytes = dom_windows * (3.0 * (kd // 32) + 4.0 * 512) + 2.0 * 2.0 * 512 * kd
+        design_bytes = dom_windows * kd * 4.0 + 2.0 * 2.0 * 512 * kd + dom_windows * 512 * 4.0
+        n_rows = int(last["rows"].shape[0])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": conf["scaling"], "vs_baseline": None,
             "dtype": "f32 (fc1: fp16x2-split operands, 3 tcgen05 MMAs, fp32 accumulate)" if args.fc1 == "tensor" else "f32",
             "data": "synthetic",
-            "config": {"workload": "BASELINE config 2 batched: %d synthetic 640x480 frames per GPU and step, full pyramid "
-                                   "(factor 1.1, min_window_length 0.075, 24 levels, 5061 windows/frame), 3-stage 12/24/48 "
-                                   "cascade with bottleneck reuse, Xavier random-init weights, thresholds 0.5, "
-                                   "groupRectangles(min_neighbors=1)" % B,
-                       "frames_per_step_per_gpu": B, "l2": "256 MiB flush buffer written between timed steps",
-                       "fc1_impl": args.fc1, "parallelism": "image-sharded replicas x%d, NCCL all-gather of detections" % world},
-            "windows_per_s": value * WINDOWS_PER_FRAME,
-            "single_frame": {"ms_per_frame": ms_one, "frames_per_s": 1000.0 / ms_one,
-                             "note": "one 640x480 frame per call (no batching): 5061 windows fill < 1 wave of 148 SMs"},
-            "stage_in": res.stage_in, "stage_kept": res.stage_kept,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * FRAME_H * FRAME_W * 3,
-                    "d2h_bytes_per_step": d2h, "boxes_per_step": n_boxes, "api": "InferenceCascadeApp.run_inference_on_images(merge=True)"},
+            "config": {"workload": conf["text"] % B, "config_id": cid, "frames_per_step": frames_step,
+                       "l2": "256 MiB flush buffer written between timed steps", "fc1_impl": args.fc1,
+                       "parallelism": "image-sharded replicas x%d, one NCCL all-gather of detections per step" % world,
+                       "host_cores_per_rank": len(cores) if cores else None},
+            "windows_per_s": value * conf["windows"],
+            "stage_in": last["in"], "stage_kept": last["kept"],
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * (world if conf["scaling"] == "weak" else 1),
+                    "d2h_bytes_per_step": n_rows * 48 + 48, "boxes_per_step": int(last["e2e_rows"].shape[0]),
+                    "api": "dist.run_sharded(InferenceCascadeApp.run_inference_on_images(merge=True)); host frames in pinned memory",
+                    "ratio_to_resident": e2e / value if value else None},
             "gpu_launches": launches,
+            "gpu_launches_source": "rodc_launch_count(): counted inside librodc at every kernel launch, difference over the timed region",
             "clocks": clocks,
-            "roofline": {"kernel": "rodc::tc::fc1_tc2_kernel (cta_group::2 pairs)" if args.fc1 == "tensor" else "rodc::fc1_simt_kernel",
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": kernel_name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
-                         # ncu --set full, same launch shape (profiles/r1h_ncu_full_fc1_pair.txt): dram read + write
-                         "traffic": NCU_FC1_TRAFFIC_BYTES if abs(dom_windows - 18944) < 1 else None,
-                         "algorithmic_bytes": dom_windows * 73728 * 4 + 512 * 73728 * 4 + dom_windows * 512 * 4,
+                         "traffic": tr["dram_bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                         "algorithmic_bytes": alg_bytes, "design_bytes": design_bytes,
+                         "design_over_algorithmic": design_bytes / alg_bytes if alg_bytes else None,
                          "peak_source": "%s bf16_tflops_sustained / 3 (each product = 3 fp16 MMAs); the denominator is cuBLAS "
                                         "running back to back for 4 s (SM clock ~1.33 GHz under the power cap), this step "
                                         "alternates fc1 with lighter kernels and holds a higher clock, so frac can exceed 1" % which,
-                         "frac_of_burst_peak": (achieved / (peak_burst / 3.0)) if peak_burst else None,
-                         "shape": "m=%d windows x K=73728 x N=512 per launch" % int(round(dom_windows)),
+                         "frac_of_burst_peak": (achieved / (peak_burst / 3.0)) if (peak_burst and peak) else None,
+                         "shape": shape + " per launch",
                          "launches": int(dom_n.value), "avg_launch_ms": dom_ms.value / max(int(dom_n.value), 1),
                          "all_fc1_launches": int(fc1_n.value), "all_fc1_achieved": achieved_all,
                          "share_of_step": fc1_ms.value / ms_total if ms_total else None,
                          "mma_per_product": mma_per_product,
-                         # one `ncu --set full` capture of this kernel on this shape (profiles/r1h_ncu_full_fc1_pair.txt)
-                         "ncu": {"tensor_pipe_active": 0.97, "sm_clock_ghz_in_kernel": 1.33,
-                                 "note": "the tensor pipe is saturated; the clock is what the 1 kW power cap leaves"}
-                         if args.fc1 == "tensor" else None},
+                         "ncu": {k: tr[k] for k in ("tensor_pipe_active", "sm_clock_ghz") if k in tr} if tr else None},
         }
+        if single:
+            line["single_frame"] = single
+        if ktable:
+            out = []
+            for r in sorted(ktable, key=lambda r: -r["ms"]):
+                ms_step = r["ms"] / k_steps
+                tensor = r["kc"] in (6, 7)
+                if tensor:
+                    ach = r["flops"] / (r["ms"] / 1000.0) / 1e12 if r["ms"] > 0 else 0.0
+                    pk = peak_tf / (3.0 if r["kc"] == 6 else 1.0)
+                    row = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "frac": ach / pk}
+                else:
+                    ach = r["bytes"] / (r["ms"] / 1000.0) / 1e9 if r["ms"] > 0 else 0.0
+                    row = {"bound": "hbm", "achieved": ach, "unit": "GB/s", "frac": ach / peak_hbm}
+                row.update({"kernel": r["name"] + (" S=%d" % r["side"] if r["side"] else ""), "ms_per_step": ms_step,
+                            "share": ms_step / ktable_step_ms if ktable_step_ms else None, "launches_per_step": r["launches"] / k_steps})
+                out.append(row)
+            line["kernels"] = out
+            line["kernels_note"] = ("device time per kernel class summed from cudaEvent pairs inside librodc (profile level 2) over %d "
+                                    "extra steps of %.2f ms; bytes / FLOPs are SURVEY.md §8(d)'s algorithmic figures, except K2a "
+                                    "features whose bytes are the materialised fc1 operand it writes (4 B / feature)" % (k_steps, ktable_step_ms))
+            tot_fl = sum(r["flops"] for r in ktable if r["kc"] in (6, 7)) / k_steps
+            line["step_fraction"] = {"algorithmic_tflops": tot_fl / (ms_total / args.steps / 1000.0) / 1e12,
+                                     "frac_of_split_tensor_peak": tot_fl / (ms_total / args.steps / 1000.0) / 1e12 / (peak_tf / 3.0)}
         if not args.no_cpu_baseline and world == 1:
-            fps, done, cores = cpu_port_time(3, budget_s=20.0)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+            fps, done, ccores = cpu_port_time(cid, 3, budget_s=20.0, offset0=offset0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": ccores, "kind": "port",
                                     "sample": "%d frame(s) of the same workload, whole path (oracle/cascade.py: Python "
                                               "extraction loops + Pillow + cv2 + torch-CPU fp32)" % done}
         print(json.dumps(line), flush=True)

@@ -46,6 +46,18 @@ class WindowOrigin:
     groups: Optional[List[dict]] = None
 
 
+@dataclass
+class MixedFrames:
+    """Device-resident frames of several shapes (``CascadeEngine.upload_mixed``): ``flat`` holds the frames
+    grouped by shape, ``offs`` / ``shapes`` the byte offset and (H, W) of every frame in internal order,
+    ``groups`` the frame count per shape (insertion order), ``order`` internal id -> index of the caller's list."""
+    flat: torch.Tensor
+    offs: List[int]
+    shapes: List[Tuple[int, int]]
+    groups: Dict[Tuple[int, int], int]
+    order: List[int]
+
+
 class CascadeEngine:
     """Runs a list of ``native.Stage`` over frame batches.  ``single=True`` applies the
     single-net decision rule (argmax != background, confidence = p[argmax])."""
@@ -164,6 +176,25 @@ class CascadeEngine:
             raise native._lib.RodcError("rodc_window_scaled_rows: bad level slot")
         self._keepalive2 = (buf, slots, dense, win_off, win_pitch)
         return native.make_source(gather_base=buf, win_off=win_off, win_pitch=win_pitch)
+
+    def _pinned_stage(self, nbytes: int) -> torch.Tensor:
+        """The pinned staging buffer (grown on demand).  Before it is handed out again the H2D copies issued from
+        it by the previous user must have finished: they are asynchronous and the host is about to overwrite it."""
+        ev = getattr(self, "_pinned_busy", None)
+        if ev is not None:
+            ev.synchronize()
+            self._pinned_busy = None
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+            self._pinned = buf
+        return buf
+
+    def _pinned_issued(self):
+        """Call after the last asynchronous copy out of the staging buffer has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pinned_busy = ev
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
@@ -289,10 +320,7 @@ class CascadeEngine:
         n = len(frames)
         h, w, _ = frames[0].shape
         need = n * h * w * 3
-        buf = getattr(self, "_pinned", None)
-        if buf is None or buf.numel() < need:
-            buf = torch.empty((need,), dtype=torch.uint8).pin_memory()
-            self._pinned = buf
+        buf = self._pinned_stage(need)
         view = buf[:need].view(n, h, w, 3)
         dst = view.numpy()
         if n >= 4:                                   # memcpy releases the GIL: gather with a few threads
@@ -327,10 +355,7 @@ class CascadeEngine:
                     dev[i].copy_(t, non_blocking=True)
             self._keepalive_host = tens
             return dev
-        buf = getattr(self, "_pinned", None)
-        if buf is None or buf.numel() < need:
-            buf = torch.empty((need,), dtype=torch.uint8).pin_memory()
-            self._pinned = buf
+        buf = self._pinned_stage(need)
         host = buf[:need].view(n, h, w, 3)
         dst = host.numpy()
         with torch.cuda.device(self.device):
@@ -351,6 +376,7 @@ class CascadeEngine:
                     for i in range(g0, g1):
                         dst[i] = frames[i]
                 dev[g0:g1].copy_(host[g0:g1], non_blocking=True)
+            self._pinned_issued()
         return dev
 
     def run_frames(self, frames, keep_trace: bool = False) -> GroupResult:
@@ -359,7 +385,9 @@ class CascadeEngine:
         with torch.cuda.device(self.device):
             if isinstance(frames, np.ndarray):
                 frames = self.stage_host_frames([frames[i] for i in range(frames.shape[0])])
-            if not frames.is_cuda:                  # pinned host batch -> one async H2D copy
+                frames = frames.to(self.device, non_blocking=True)      # pinned host batch -> one async H2D copy
+                self._pinned_issued()
+            elif not frames.is_cuda:
                 frames = frames.to(self.device, non_blocking=True)
             assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
             frames = frames.contiguous()
@@ -386,40 +414,51 @@ class CascadeEngine:
                                       groups=[dict(frames=frames, frame_base=0, scales=plan.scale, width=plan.win)])
             return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, origin)
 
-    def run_mixed(self, frames: Sequence[np.ndarray], keep_trace: bool = False) -> Tuple[GroupResult, List[int]]:
-        """Whole path for host frames of DIFFERENT shapes in one set of stage launches (the reference's
-        merge mode concatenates the windows of all images, `app/abstract_inference_app.py:66-81`).
-        One K1 launch pair per shape writes into a shared pyramid buffer; stage 0 reads its windows
-        through a per-window (offset, pitch) table, later stages re-crop from a table of all frames.
-        Returns the result with INTERNAL frame ids (grouped by shape) and ``order``: internal id -> index
-        into ``frames``.  Every frame must yield windows (callers filter with ``plan_for``)."""
+    def upload_mixed(self, frames: Sequence[np.ndarray]) -> "MixedFrames":
+        """Host frames of DIFFERENT shapes -> one flat device buffer (frames grouped by shape, one asynchronous
+        H2D copy from the pinned staging buffer) plus the bookkeeping ``run_mixed_device`` needs."""
         with torch.cuda.device(self.device):
             groups: Dict[Tuple[int, int], List[int]] = {}
             for i, f in enumerate(frames):
                 groups.setdefault((f.shape[0], f.shape[1]), []).append(i)
             order = [i for idx in groups.values() for i in idx]
-            plans = {k: self.plan_for(k[1], k[0]) for k in groups}
-            for k, p in plans.items():
-                if p.n_windows < 1:
-                    raise ValueError("Could not extract any windows from the given image")
-                if not p.fits:
-                    raise ValueError("xmax/ymax must not leave the image boundaries")
             # one pinned buffer with all frames (group order) -> one H2D copy
             sizes = [frames[i].size for i in order]
             total = int(sum(sizes))
-            buf = getattr(self, "_pinned", None)
-            if buf is None or buf.numel() < total:
-                buf = torch.empty((total,), dtype=torch.uint8).pin_memory()
-                self._pinned = buf
+            buf = self._pinned_stage(total)
             host = buf[:total].numpy()
             offs, o = [], 0
             for i, sz in zip(order, sizes):
                 host[o:o + sz] = frames[i].reshape(-1)
                 offs.append(o); o += sz
             flat = buf[:total].to(self.device, non_blocking=True)
-            table = native.FrameTable(flat, offs, [(frames[i].shape[0], frames[i].shape[1]) for i in order])
-            n_windows = sum(len(idx) * plans[k].n_windows for k, idx in groups.items())
-            pyr_bytes = sum(len(idx) * plans[k].pyramid_bytes for k, idx in groups.items())
+            self._pinned_issued()
+            return MixedFrames(flat=flat, offs=offs, shapes=[(frames[i].shape[0], frames[i].shape[1]) for i in order],
+                               groups={k: len(v) for k, v in groups.items()}, order=order)
+
+    def run_mixed(self, frames: Sequence[np.ndarray], keep_trace: bool = False) -> Tuple[GroupResult, List[int]]:
+        """Whole path for host frames of DIFFERENT shapes in one set of stage launches (the reference's
+        merge mode concatenates the windows of all images, `app/abstract_inference_app.py:66-81`).
+        Returns the result with INTERNAL frame ids (grouped by shape) and ``order``: internal id -> index
+        into ``frames``.  Every frame must yield windows (callers filter with ``plan_for``)."""
+        mf = self.upload_mixed(frames)
+        return self.run_mixed_device(mf, keep_trace), mf.order
+
+    def run_mixed_device(self, mf: "MixedFrames", keep_trace: bool = False) -> GroupResult:
+        """``run_mixed`` for frames that are already resident (``upload_mixed``).  One K1 launch pair per shape
+        writes into a shared pyramid buffer; stage 0 reads its windows through a per-window (offset, pitch)
+        table, later stages re-crop from a table of all frames."""
+        with torch.cuda.device(self.device):
+            flat, offs = mf.flat, mf.offs
+            plans = {k: self.plan_for(k[1], k[0]) for k in mf.groups}
+            for k, p in plans.items():
+                if p.n_windows < 1:
+                    raise ValueError("Could not extract any windows from the given image")
+                if not p.fits:
+                    raise ValueError("xmax/ymax must not leave the image boundaries")
+            table = native.FrameTable(flat, offs, mf.shapes)
+            n_windows = sum(n * plans[k].n_windows for k, n in mf.groups.items())
+            pyr_bytes = sum(n * plans[k].pyramid_bytes for k, n in mf.groups.items())
             pyr = torch.empty((pyr_bytes,), dtype=torch.uint8, device=self.device)
             win_off = torch.empty((n_windows,), dtype=torch.int64, device=self.device)
             win_pitch = torch.empty((n_windows,), dtype=torch.int32, device=self.device)
@@ -429,8 +468,8 @@ class CascadeEngine:
             slot_groups: List[dict] = []
             fbase = wbase = pbase = sbase = 0
             pos = 0
-            for k, idx in groups.items():
-                p, n = plans[k], len(idx)
+            for k, n in mf.groups.items():
+                p = plans[k]
                 fsz = k[0] * k[1] * 3
                 d = flat[offs[pos]:offs[pos] + n * fsz].view(n, k[0], k[1], 3)
                 native.pyramid(p, d, out=pyr[pbase:pbase + n * p.pyramid_bytes].view(n, p.pyramid_bytes))
@@ -445,7 +484,7 @@ class CascadeEngine:
             src0 = native.make_source(gather_base=pyr, win_off=win_off, win_pitch=win_pitch)
             self._keepalive0 = (pyr, win_off, win_pitch, flat, table)
             origin = WindowOrigin(gather=lambda: (pyr, win_off, win_pitch), slot=slot0, groups=slot_groups)
-            return self._run_stages(src0, n_windows, meta0, table, len(order), keep_trace, origin), order
+            return self._run_stages(src0, n_windows, meta0, table, len(mf.order), keep_trace, origin)
 
     def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False,
                     scales: Optional[np.ndarray] = None, widths: Optional[np.ndarray] = None) -> GroupResult:

@@ -89,7 +89,14 @@ class StageModel:
         return self.fc1_size + self.n_prev
 
     def save(self, path: str):
+        """``.npz``: this package's container; ``.pb``: a GraphDef with the reference's node names and op
+        attributes (`network/graph_pb.py`)."""
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        if path.endswith(".pb"):
+            from .graph_pb import write_stage_pb
+            write_stage_pb(path, self.weights, self.n_prev > 0, self.in_size, self.conv_stride, self.pool_size,
+                           self.pool_stride)
+            return
         with open(path, "wb") as f:
             np.savez(f, in_size=self.in_size, conv_stride=self.conv_stride, pool_size=self.pool_size,
                      pool_stride=self.pool_stride, **self.weights)
@@ -97,8 +104,10 @@ class StageModel:
     @staticmethod
     def load(path: str) -> "StageModel":
         if path.endswith(".pb"):
-            from .graph_pb import read_stage_pb
-            return StageModel(read_stage_pb(path))
+            # weights from the Const nodes, geometry from the X placeholder / Conv2D / MaxPool attributes
+            from .graph_pb import read_stage_graph
+            weights, geo = read_stage_graph(path)
+            return StageModel(weights, **geo)
         with np.load(path) as z:
             d = {k: z[k] for k in z.files}
         geo = {k: int(d.pop(k)) for k in ("in_size", "conv_stride", "pool_size", "pool_stride") if k in d}

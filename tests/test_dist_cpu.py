@@ -66,6 +66,77 @@ def test_sharded_run_gathers_all_detections_in_order():
                [[tuple(float(v) for v in b) for b in per] for per in expect]
 
 
+class _FailingApp(_FakeApp):
+    """Rank 1's shard has no usable image: the app raises like `app/abstract_inference_app.py:106-107`."""
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def run_inference_on_images(self, images, merge=True):
+        if self.rank == 1:
+            raise ValueError("Could not extract any windows from the given image")
+        return super().run_inference_on_images(images, merge)
+
+
+class _ManyBoxesApp(_FakeApp):
+    """More detections than the initial exchange capacity: the block must grow on every rank alike."""
+
+    def run_inference_on_images(self, images, merge=True):
+        return [[_FakeBox((j, k, j + 1, k + 1, 1.0)) for k in range(3000)] for j in images]
+
+
+def _worker_edge(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from rapidobjectdetectionusingcascadedcnns_b200 import dist as rdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rdist.run_sharded(_FailingApp(rank), list(range(6)))
+        failed = None
+    except rdist.ShardError as e:
+        failed = str(e)
+    rows = rdist.run_sharded(_ManyBoxesApp(), list(range(4)), as_rows=True)     # 2 x 3000 rows per rank > 4096
+    q.put((rank, failed, rows.shape, float(rows[:, 0].min()), float(rows[:, 0].max()),
+           bool((np.diff(rows[:, 0]) >= 0).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_failing_rank_raises_everywhere_and_capacity_grows():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_edge, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, failed, shape, lo, hi, sorted_ok in got:
+        assert failed is not None and "rank(s) [1]" in failed          # nobody hangs, everybody learns who failed
+        assert shape == (12000, 6) and (lo, hi) == (0.0, 3.0) and sorted_ok
+
+
+def test_bind_rank_to_cores_slices_the_affinity_set():
+    from rapidobjectdetectionusingcascadedcnns_b200 import dist as rdist
+    if not hasattr(os, "sched_getaffinity"):
+        return
+    before = os.sched_getaffinity(0)
+    try:
+        got = rdist.bind_rank_to_cores(1, 2)
+        if len(before) >= 4:
+            avail = sorted(before)
+            per = len(avail) // 2
+            assert got == avail[per:2 * per] and os.sched_getaffinity(0) == set(got)
+        else:
+            assert got is None
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 def test_single_process_is_passthrough():
     from rapidobjectdetectionusingcascadedcnns_b200 import dist as rdist
     rows = np.arange(12, dtype=np.float64).reshape(2, 6)

@@ -14,7 +14,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-EPS = [1e-4, 2e-4, 4e-4]
+# north_star: survivor sets may differ from the fp64 oracle only for windows whose logit margin lies within 1e-4 of
+# the threshold, at every stage
+EPS = [1e-4, 1e-4, 1e-4]
 
 
 @pytest.fixture()
@@ -99,7 +101,7 @@ def test_config4_1080p_dense_pyramid(pkg):
 
 
 def test_config5_4k_high_reject_properties(pkg):
-    from oracle import cascade as oc, group_rectangles as gr, stage_net
+    from oracle import cascade as oc, stage_net
     from rapidobjectdetectionusingcascadedcnns_b200 import native, synth
     from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine
     cfd = dict(min_window_length=0.0125)
@@ -139,18 +141,41 @@ def test_config5_4k_high_reject_properties(pkg):
     # the sampled raw windows equal the oracle's extraction (pyramid + grid at 4K)
     raw_ref, _ = oc.extract_windows(frames[1], 12, ocfg, "lib")
     assert np.array_equal(wins[sample], raw_ref[sample])
-    # K5 against the oracle on the GPU's own final candidates
-    meta = res.trace["meta"][-1].cpu().numpy()
-    kfin = res.trace["keep"][-1].cpu().numpy()
-    cand = meta[kfin]
-    out = []
-    for f in range(2):
-        c = cand[cand[:, 0] == f]
-        rr, ww = gr.group_rectangles([(r[1], r[2], r[3] - r[1], r[4] - r[2]) for r in c], 1)
-        out += [[f, r[0], r[1], r[0] + r[2], r[1] + r[3], w] for r, w in zip(rr, ww)]
-    ref = np.asarray(out, np.float64).reshape(-1, 6)
-    got = np.column_stack([res.frame, res.boxes, res.conf]).astype(np.float64).reshape(-1, 6)
-    assert np.array_equal(got, ref)
+    # stages 1-2 and the final boxes against the fp64 oracle, continued from the stage-0 survivors (a few hundred
+    # windows): bottleneck chain, cv2.resize re-crops, thresholds, groupRectangles
+    wins0 = native.extract_windows(plan, native.pyramid(plan, d[0:1])).cpu().numpy()
+    surv = keep0
+    raw = np.stack([(wins0 if w < 161969 else wins)[w % 161969] for w in surv.tolist()])
+    meta = res.trace["meta"][0].cpu().numpy()[surv]                    # (frame, *_norm box) of the survivors
+    assert np.array_equal(meta[:, 0], surv // 161969)
+    _, bott, _, _ = stage_net.stage_forward(raw, weights[0], None, dtype=torch.float64)
+    same = True
+    for i in (1, 2):
+        size = 12 * 2 ** i
+        raw = np.stack([oc.recrop(frames[m[0]], m[1:5], size, "lib") for m in meta]) if len(meta) else \
+            np.zeros((0, size, size, 3), np.uint8)
+        assert i < len(res.trace["X"]) or len(meta) == 0
+        if len(meta) == 0:
+            break
+        assert np.array_equal(res.trace["X"][i].cpu().numpy(), raw), "stage %d input differs" % i
+        p64, bott, l64, _ = stage_net.stage_forward(raw, weights[i], bott, dtype=torch.float64)
+        l64 = l64.numpy()
+        lg = res.trace["logits"][i].cpu().numpy()
+        assert np.abs(lg - l64).max() <= 1e-3 * np.abs(l64).max()
+        keep = np.nonzero(p64.numpy()[:, 1] > 0.5)[0]
+        keep_gpu = res.trace["keep"][i].cpu().numpy()
+        diff = np.setxor1d(keep, keep_gpu)
+        if diff.size:
+            assert np.abs(l64[diff, 1] - l64[diff, 0]).max() < EPS[i], "stage %d flip outside the band" % i
+            same = False
+            break
+        meta, bott = meta[keep], bott[keep]
+    if same:
+        # final boxes: groupRectangles per frame over the ORACLE's candidates (= the GPU's, survivor sets match)
+        boxes, conf, image = oc.postprocess(meta[:, 1:5].astype(np.int64), np.ones(len(meta)), meta[:, 0].astype(np.int64), ocfg, "restated")
+        ref = np.column_stack([image, boxes, conf]).astype(np.float64).reshape(-1, 6)
+        got = np.column_stack([res.frame, res.boxes, res.conf]).astype(np.float64).reshape(-1, 6)
+        assert np.array_equal(got, ref)
 
 
 def test_config1_single_net_640x480(pkg):

@@ -229,12 +229,14 @@ def test_stage_forward_matches_fp64_oracle(nat, stage_idx, impl_name):
     assert np.abs(got_b[:, :512] - b64[:, :512]).max() <= 2e-5 * scale_b
     err = np.abs(got_l - l64)
     assert err.max() <= 2e-5 * np.abs(l64).max(), (err.max(), np.abs(l64).max())
-    # margin (the quantity the threshold acts on): inside the per-stage epsilon band (1e-4 at K = 4608,
-    # growing with sqrt(K) like any fp32 accumulation -- the reference's own Eigen GEMM included)
+    # margin (the quantity the threshold acts on): inside north_star's epsilon band of 1e-4 at EVERY stage.
+    # Measured maxima on B200 for this sample (stages 0 / 1 / 2): tensor 6.1e-5 / 9.4e-5 / 6.2e-5, plain fp32 FMA
+    # (the arithmetic class of the reference's own Eigen GEMM) 4.1e-5 / 5.6e-5 / 7.4e-5 -- the floor is the fp32
+    # rounding of the 512..1536 bottleneck values that fc2 sums, not the tensor path.
     m_err = np.abs((got_l[:, 1] - got_l[:, 0]) - (l64[:, 1] - l64[:, 0]))
     print("stage %d %s: max |logit err| %.3g, max |margin err| %.3g, max |fc1 err| %.3g" % (
         stage_idx, impl_name, err.max(), m_err.max(), np.abs(got_b[:, :512] - b64[:, :512]).max()))
-    assert m_err.max() < [1e-4, 2e-4, 4e-4][stage_idx], m_err.max()
+    assert m_err.max() < 1e-4, m_err.max()
     np.testing.assert_allclose(probs.cpu().numpy(), p64.numpy(), rtol=1e-3, atol=1e-6)
 
 

@@ -70,6 +70,57 @@ def test_stage_model_files_roundtrip(tmp_path):
         StageModel({k: v for k, v in ws[0].items() if k != "fc2_b"})
 
 
+def test_pb_reader_on_tf_shaped_exports(tmp_path):
+    """A GraphDef shaped like the reference's export (`app/train_app.py:177-227`): op nodes present, an
+    ``import/`` scope, the ``<var>/read`` Identity nodes of an un-optimised freeze.  Weights come from the Const
+    nodes, geometry from X / Conv2D / MaxPool -- including a non-default pooling that leaves the flattened size
+    unchanged (5x5 / stride 1) and a strided net."""
+    from rapidobjectdetectionusingcascadedcnns_b200 import StageModel, synth
+    from rapidobjectdetectionusingcascadedcnns_b200.network.graph_pb import read_stage_graph, write_stage_pb
+    from tensorboard.compat.proto import graph_pb2
+    w1 = synth.xavier_stage_weights(1, 24, n_prev_bottleneck=512)
+    pb = str(tmp_path / "graph_tf_1.pb")
+    write_stage_pb(pb, w1, True, 24, prefix="import/", identity_reads=True)
+    gd = graph_pb2.GraphDef(); gd.ParseFromString(open(pb, "rb").read())
+    ops = {n.op for n in gd.node}
+    assert {"Placeholder", "Const", "Identity", "Conv2D", "BiasAdd", "Relu", "MaxPool", "Reshape", "MatMul", "ConcatV2",
+            "Softmax"} <= ops
+    names = {n.name for n in gd.node}
+    assert {"import/X", "import/bottleneck_in", "import/bottleneck_out_part1/W", "import/bottleneck_out_part1/W/read",
+            "import/bottleneck_out/Relu", "import/final_softmax", "import/conv_layer_0/conv",
+            "import/pool_layer_0/MaxPool"} <= names
+    m = StageModel.load(pb)
+    assert all(np.array_equal(m.weights[k], w1[k]) for k in m.weights)
+    assert (m.in_size, m.conv_stride, m.pool_size, m.pool_stride, m.n_prev) == (24, 1, 3, 1, 512)
+    # another pooling size with the same flattened size must NOT be read as the default 3x3
+    pb5 = str(tmp_path / "graph_pool5_0.pb")
+    w0 = synth.xavier_stage_weights(0, 12)
+    write_stage_pb(pb5, w0, False, 12, pool_size=5)
+    assert StageModel.load(pb5).pool_size == 5
+    # strided net: 24 -> conv stride 2 -> 12 -> pool stride 2 -> 6; K = 6*6*32
+    ws = dict(w0); rs = np.random.RandomState(3)
+    ws["fc1_W"] = rs.uniform(-0.01, 0.01, (6 * 6 * 32, 512)).astype(np.float32)
+    pbs = str(tmp_path / "graph_strided_0.pb")
+    write_stage_pb(pbs, ws, False, 24, conv_stride=2, pool_stride=2)
+    ms = StageModel.load(pbs)
+    assert (ms.in_size, ms.conv_stride, ms.pool_stride, ms.weights["fc1_W"].shape[0]) == (24, 2, 2, 1152)
+    # a Const-only file carries no geometry: refuse to guess
+    bare = str(tmp_path / "graph_bare_0.pb")
+    write_stage_pb(bare, w0, False, 12, ops=False)
+    with pytest.raises(ValueError, match="refusing to guess"):
+        read_stage_graph(bare)
+    # geometry that contradicts the weights is an error, not a silent default
+    bad = str(tmp_path / "graph_bad_0.pb")
+    write_stage_pb(bad, w0, False, 16)
+    with pytest.raises(ValueError):
+        StageModel.load(bad)
+    # StageModel.save(.pb) round trip incl. geometry
+    out = str(tmp_path / "graph_rt_0.pb")
+    ms.save(out)
+    r = StageModel.load(out)
+    assert (r.in_size, r.conv_stride, r.pool_stride) == (24, 2, 2) and np.array_equal(r.weights["fc1_W"], ws["fc1_W"])
+
+
 def test_cascade_app_model_discovery_errors(tmp_path):
     import rapidobjectdetectionusingcascadedcnns_b200 as pkg
     pkg.cf.reset()
