@@ -251,8 +251,10 @@ def main():
     pkg.cf.set("fc1_impl", args.fc1)
     for k, v in conf["cf"].items():
         pkg.cf.set(k, v)
-    if cid in (4, 5):
-        pkg.cf.set("max_windows_per_launch", 1 << 22)       # 2.2 KB of stage-0 state per window: 9 GB of the 180 GB
+    if cid in (3, 4, 5):
+        # 2.2 KB of stage-0 state per window: 9 GB of the 180 GB.  Config 3: ~650 frames per launch set, so every one
+        # of the 35 shapes brings ~18 frames to its pyramid launch instead of one
+        pkg.cf.set("max_windows_per_launch", 1 << 22)
 
     ids, total_frames = my_frame_ids(cid, B, rank, world)
     host_frames = [synth.synth_frame(*frame_spec(cid, j)) for j in ids]

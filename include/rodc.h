@@ -191,6 +191,23 @@ int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, int impl);
 int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
                        float* bottleneck, int ld_bott, float* logits, float* probs,
                        void* workspace, int64_t workspace_bytes, int impl, void* stream);
+/* Device-side counts ("_dyn" entry points).  n is an UPPER BOUND that sizes buffers and grids; the number of
+ * windows actually processed is min(n, *n_dev), read on the device when the kernels run (n_dev = the count_out of
+ * the previous stage's rodc_compact_dyn; NULL = n).  Rows past the count are neither read nor written.  With
+ * these three calls a whole cascade is enqueued without a host round trip per stage and can be captured in a
+ * CUDA graph (the reference learns every survivor count on the host, inference_cascade_app.py:219-247).
+ * Tensor fc1 only. */
+int rodc_stage_forward_dyn(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
+                           const int64_t* n_dev, float* bottleneck, int ld_bott, float* logits, float* probs,
+                           void* workspace, int64_t workspace_bytes, int impl, void* stream);
+int rodc_compact_dyn(const float* probs, int64_t n, const int64_t* n_dev, double threshold,
+                     const int32_t* meta_in, int32_t* meta_out,
+                     const float* bott_in, int ld_in, int width, float* bott_out, int ld_out, int col_off,
+                     const float* conf_acc_in, float* conf_out, int conf_mode,
+                     int32_t* keep_idx_out, int64_t* count_out, void* scratch, void* stream);
+int rodc_group_rectangles_dyn(const int32_t* cand, int64_t k, const int64_t* k_dev, int n_frames, int min_neighbors,
+                              double eps, int32_t* out, int64_t* out_count, void* scratch, void* stream);
+
 /* Test hook: pooled conv features of the windows, fp32 [n, in*in*C] (NHWC flatten order). */
 int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, int64_t first,
                             int64_t n, float* features, void* stream);

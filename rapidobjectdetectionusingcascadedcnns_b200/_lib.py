@@ -67,6 +67,11 @@ SIGNATURES = {
     "rodc_stage_workspace_bytes": (C.c_int64, [vp, C.c_int64, C.c_int]),
     "rodc_stage_forward": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, C.c_int, vp, vp,
                                      vp, C.c_int64, C.c_int, vp]),
+    "rodc_stage_forward_dyn": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, vp, C.c_int, vp, vp,
+                                         vp, C.c_int64, C.c_int, vp]),
+    "rodc_compact_dyn": (C.c_int, [vp, C.c_int64, vp, C.c_double, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+                                   vp, vp, C.c_int, vp, vp, vp, vp]),
+    "rodc_group_rectangles_dyn": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp]),
     "rodc_stage_features_f32": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, vp]),
     "rodc_compact_scratch_bytes": (C.c_int64, [C.c_int64]),
     "rodc_compact": (C.c_int, [vp, C.c_int64, C.c_double, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,

@@ -20,6 +20,9 @@ MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT = 0.5001
 # librodc-specific switches (not in the reference)
 FC1_IMPL_TENSOR = "tensor"        # tcgen05 split-fp16 GEMM
 FC1_IMPL_SIMT = "simt"            # fp32 CUDA-core GEMM (cross-check)
+LATENCY_AUTO = "auto"             # small batches run as one CUDA graph with device-side survivor counts
+LATENCY_ALWAYS = "always"
+LATENCY_OFF = "off"
 
 
 def _defaults():
@@ -73,6 +76,8 @@ def _defaults():
     # librodc
     cf["fc1_impl"] = FC1_IMPL_TENSOR
     cf["max_windows_per_launch"] = 1 << 18                 # frame batches are cut so stage 0 stays below this
+    cf["latency_mode"] = LATENCY_AUTO                      # engine.run_frames_latency for batches of <= latency_max_windows
+    cf["latency_max_windows"] = 16384                      # stage-0 windows (one 640x480 frame has 5061)
     return cf
 
 

@@ -25,6 +25,17 @@ void set_error(const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Device-side element counts.  A launch sized for an upper bound n reads the real count from device memory
+// (written by rodc_compact of the previous stage), so a whole cascade can be enqueued -- or captured in a CUDA
+// graph -- without the host ever learning a survivor count: effective n = clamp(*n_dev - off, 0, n).
+#ifdef __CUDACC__
+__device__ __forceinline__ int64_t eff_count(int64_t n, const int64_t* n_dev, int64_t off = 0) {
+    if (!n_dev) return n;
+    const int64_t v = *n_dev - off;
+    return v < 0 ? 0 : (v < n ? v : n);
+}
+#endif
+
 // Kernel classes of the launch accounting / measurement hook (prof.cu, rodc_profile_table).
 enum KernelClass { KC_PYR_H = 0, KC_PYR_V, KC_WINTAB, KC_SOURCE, KC_RECROP, KC_FEAT, KC_FC1, KC_FC1_SIMT, KC_FC2,
                    KC_COMPACT, KC_GROUP, KC_MISC, KC_COUNT };

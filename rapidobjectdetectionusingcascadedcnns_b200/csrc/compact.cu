@@ -23,9 +23,10 @@ __device__ __forceinline__ bool keep_pred(const float* probs, int64_t w, int64_t
     return (double)probs[2 * w + 1] > thr;
 }
 
-__global__ void __launch_bounds__(CT) compact_count_kernel(const float* __restrict__ probs, int64_t n, double thr,
-                                                           int32_t* __restrict__ tile_count) {
+__global__ void __launch_bounds__(CT) compact_count_kernel(const float* __restrict__ probs, int64_t n, const int64_t* __restrict__ n_dev,
+                                                           double thr, int32_t* __restrict__ tile_count) {
     __shared__ int warp_cnt[CT / 32];
+    n = eff_count(n, n_dev);
     const int64_t w = (int64_t)blockIdx.x * CT + threadIdx.x;
     const unsigned b = __ballot_sync(0xffffffffu, keep_pred(probs, w, n, thr));
     if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
@@ -69,12 +70,13 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* __restrict_
     if (threadIdx.x == 0) *count_out = carry;
 }
 
-__global__ void __launch_bounds__(CT) compact_scatter_kernel(const float* __restrict__ probs, int64_t n, double thr,
-                                                             const int32_t* __restrict__ tile_off,
+__global__ void __launch_bounds__(CT) compact_scatter_kernel(const float* __restrict__ probs, int64_t n, const int64_t* __restrict__ n_dev,
+                                                             double thr, const int32_t* __restrict__ tile_off,
                                                              const int32_t* __restrict__ meta_in, int32_t* __restrict__ meta_out,
                                                              const float* __restrict__ conf_acc, float* __restrict__ conf_out, int conf_mode,
                                                              int32_t* __restrict__ keep_idx) {
     __shared__ int warp_cnt[CT / 32];
+    n = eff_count(n, n_dev);
     const int64_t w = (int64_t)blockIdx.x * CT + threadIdx.x;
     const bool keep = keep_pred(probs, w, n, thr);
     const unsigned b = __ballot_sync(0xffffffffu, keep);
@@ -132,6 +134,16 @@ extern "C" int rodc_compact(const float* probs, int64_t n, double threshold,
                             const float* bott_in, int ld_in, int width, float* bott_out, int ld_out, int col_off,
                             const float* conf_acc_in, float* conf_out, int conf_mode,
                             int32_t* keep_idx_out, int64_t* count_out, void* scratch, void* stream) {
+    return rodc_compact_dyn(probs, n, nullptr, threshold, meta_in, meta_out, bott_in, ld_in, width, bott_out, ld_out, col_off,
+                            conf_acc_in, conf_out, conf_mode, keep_idx_out, count_out, scratch, stream);
+}
+
+extern "C" int rodc_compact_dyn(const float* probs, int64_t n, const int64_t* n_dev, double threshold,
+                                const int32_t* meta_in, int32_t* meta_out,
+                                const float* bott_in, int ld_in, int width, float* bott_out, int ld_out, int col_off,
+                                const float* conf_acc_in, float* conf_out, int conf_mode,
+                                int32_t* keep_idx_out, int64_t* count_out, void* scratch, void* stream) {
+    RODC_CHECK_ARG(n_dev != count_out, "rodc_compact: the input count and the output count must be different buffers");
     RODC_CHECK_ARG(probs && count_out && scratch, "rodc_compact: NULL argument");
     RODC_CHECK_ARG(n >= 0 && n < (1ll << 31), "rodc_compact: bad n");
     RODC_CHECK_ARG((meta_in == nullptr) == (meta_out == nullptr), "rodc_compact: meta_in/meta_out must both be set or both NULL");
@@ -152,11 +164,11 @@ extern "C" int rodc_compact(const float* probs, int64_t n, double threshold,
     // The survivor count is data dependent: bytes are booked for the worst case n survivors of the gather.
     Prof prof(KC_COMPACT, st, width, 8.0 * (double)n + (double)n * 44.0 + (bott_in ? 8.0 * (double)n * width : 0.0), 0.0,
               bott_in ? 4 : 3);
-    compact_count_kernel<<<nt, CT, 0, st>>>(probs, n, threshold, tile);
+    compact_count_kernel<<<nt, CT, 0, st>>>(probs, n, n_dev, threshold, tile);
     RODC_LAUNCH_CHECK();
     compact_scan_kernel<<<1, 1024, 0, st>>>(tile, nt, count_out);
     RODC_LAUNCH_CHECK();
-    compact_scatter_kernel<<<nt, CT, 0, st>>>(probs, n, threshold, tile, meta_in, meta_out, conf_acc_in, conf_out, conf_mode, keep_idx_out);
+    compact_scatter_kernel<<<nt, CT, 0, st>>>(probs, n, n_dev, threshold, tile, meta_in, meta_out, conf_acc_in, conf_out, conf_mode, keep_idx_out);
     RODC_LAUNCH_CHECK();
     if (bott_in) {
         int64_t blocks = (n + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;

@@ -68,11 +68,12 @@ __global__ void __launch_bounds__(256) fc1_simt_kernel(const float* __restrict__
 // One warp per window.  fp64 accumulation (the fp64 oracle is the arbiter; TF's own fp32 order is
 // unspecified), logits rounded to fp32, softmax in fp32 as exp(x - max) / sum.
 __global__ void __launch_bounds__(256) fc2_softmax_kernel(const float* __restrict__ bott, int ld, int width, int64_t n,
+                                                          const int64_t* __restrict__ n_dev,
                                                           const float* __restrict__ W2, const float* __restrict__ b2,
                                                           float* __restrict__ logits, float* __restrict__ probs) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= n) return;
+    if (w >= eff_count(n, n_dev)) return;
     const float* row = bott + w * ld;
     double s0 = 0.0, s1 = 0.0;
     if ((width & 127) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(bott) & 15) == 0) {
@@ -123,13 +124,14 @@ int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bo
     return RODC_OK;
 }
 
-int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st) {
+int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st,
+                       const int64_t* n_dev) {
     if (n <= 0) return RODC_OK;
     const int width = s->fc1_size + s->n_prev;
     const int wpb = 8;
     // K2c: reads the [own | prev] bottleneck row, writes logits + softmax (4 * 512 (i + 1) B / window)
     Prof prof(KC_FC2, st, s->in_size, (double)n * (4.0 * width + 16.0), (double)n * 4.0 * width);
-    fc2_softmax_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(bott, ld_bott, width, n, s->fc2_w, s->fc2_b, logits, probs);
+    fc2_softmax_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(bott, ld_bott, width, n, n_dev, s->fc2_w, s->fc2_b, logits, probs);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
               const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
-              float out_scale, int probe_hi_only) {
+              float out_scale, int probe_hi_only, const int64_t* __restrict__ m_dev, int64_t m_off) {
     using T = Tile<BN_, STAGES_>;
+    m = (int)eff_count(m, m_dev, m_off);
+    if ((int)(blockIdx.x / T::N_TILES) * BM >= m) return;       // grid sized for an upper bound of m: nothing to do
     constexpr int STAGES = STAGES_, STAGE_BYTES = T::STAGE_BYTES, B_TILE = T::B_TILE, CW = T::COLS_PER_WARP;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -311,8 +313,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const float* __restrict__ bias, float* __restrict__ out, int ld_out, int m, int num_kb, int kc,
-               float out_scale, int probe_hi_only) {
+               float out_scale, int probe_hi_only, const int64_t* __restrict__ m_dev, int64_t m_off) {
     using T = PairTile<BN_, STAGES_>;
+    m = (int)eff_count(m, m_dev, m_off);
+    if ((int)((blockIdx.x >> 1) / T::N_TILES) * (2 * BM) >= m) return;   // both CTAs of a pair leave together
     constexpr int STAGES2 = STAGES_, STAGE2_BYTES = T::STAGE_BYTES, BN_HALF = T::BN_HALF, B_HALF_TILE = T::B_HALF_TILE;
     constexpr int CW = T::COLS_PER_WARP;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -543,7 +547,7 @@ static bool fc1_narrow_tiles(unsigned m_tiles) {
 }  // namespace tc
 
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
-                      float* bott, int ld_bott, cudaStream_t st) {
+                      float* bott, int ld_bott, cudaStream_t st, const int64_t* m_dev, int64_t m_off) {
     using namespace tc;
     if (m <= 0) return RODC_OK;
     RODC_CHECK_ARG(s->fc1_size == FC1_N, "tensor fc1 is built for fc1_size == 512 (got %d)", s->fc1_size);
@@ -557,7 +561,9 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
               2.0 * (double)m * (double)s->K * (double)FC1_N);
     const unsigned m_tiles = (unsigned)((m + BM - 1) / BM);
     const float out_scale = ldexpf(1.f, -(s->a_exp + s->w_exp));
-    if (fc1_narrow_tiles(m_tiles)) {
+    // with a device-side count m is only an upper bound: CTAs past the real count exit at once, so narrow tiles are
+    // taken up to twice the one-wave threshold (a single un-batched frame whose survivors fill at most one wave)
+    if (fc1_narrow_tiles(m_dev ? (m_tiles + 1) / 2 : m_tiles)) {
         // (a pair kernel with 128-wide tiles, PairTile<128, 4>, was measured slower here: 1.07 vs 0.82 ms at m = 3456 --
         // with half the SMs' worth of CTAs the cluster handshakes outweigh the smaller operand stream)
         using T = Tile<128, 3>;
@@ -565,7 +571,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
             (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, 128)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, 128))) return rc;
         RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
         fc1_tc_kernel<128, 3><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                                  (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
+                                                                                  (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
@@ -576,7 +582,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
         RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
         const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * P::N_TILES;      // (M pairs) x (N tiles)
         fc1_tc2_kernel<256, 3><<<pairs * 2u, THREADS, P::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                           (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
+                                                                           (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
@@ -585,7 +591,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
         (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN))) return rc;
     RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     fc1_tc_kernel<256, 2><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                              (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only());
+                                                                              (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

@@ -100,8 +100,9 @@ __device__ __forceinline__ void fill_recrop_tables(const Crop& c, int S, int* ta
 // app/inference_cascade_app.py:200-202): out [n,S,S,3].  API / parity path; the stage kernels read the
 // sources in place.
 __global__ void __launch_bounds__(128) source_windows_kernel(SrcDev src, int64_t first, int64_t n, int S,
-                                                             uint8_t* __restrict__ out) {
+                                                             uint8_t* __restrict__ out, const int64_t* __restrict__ n_dev, int64_t n_off) {
     extern __shared__ int tabs[];
+    n = eff_count(n, n_dev, n_off);
     for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
         const int64_t w = first + wrel;
         uint8_t* o = out + wrel * (int64_t)S * S * 3;
@@ -156,9 +157,10 @@ __device__ __forceinline__ void load_taps(const uint8_t* p, int len, uint32_t& l
 
 template <int S, int RPP>
 __global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev src, int64_t first, int64_t n,
-                                                                       uint8_t* __restrict__ out) {
+                                                                       uint8_t* __restrict__ out, const int64_t* __restrict__ n_dev, int64_t n_off) {
     constexpr int UN = S / 4, THREADS = UN * RPP;
     __shared__ int tabs[6 * S];
+    n = eff_count(n, n_dev, n_off);
     const int u = threadIdx.x % UN, r0 = threadIdx.x / UN;
     for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
         const Crop c = make_crop(src, first + wrel);
@@ -236,6 +238,141 @@ __global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev sr
     }
 }
 
+
+// K4, staged variant (default).  The scattered tap loads of recrop_windows_kernel kept the L1 request path busy
+// (ncu: l1tex 91 %, 5.7x more bytes through L1 than written, profiles/r1j_ncu_full_recrop48_byte_loads.txt).  Here a
+// CTA first copies the source rows a band of output rows needs into shared memory with coalesced 16-byte loads
+// (only 16-byte words that contain a byte of the crop row are touched, so nothing outside the frames buffer is
+// read), then resamples from shared memory with the same integer arithmetic.  A band takes either the contiguous
+// source-row range (down-scales below 2x: consecutive output rows share source rows, each is fetched once) or the
+// two rows of every output row (larger down-scales).  Crops too wide for the staging buffer fall back to the
+// scattered kernel's tap loads.
+__device__ __forceinline__ void lds_taps(const uint8_t* row, int off, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(row + (off & ~3));
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    const int sh = (off & 3) * 8;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+template <int S, int RPP, int STAGE_BYTES>
+__global__ void __launch_bounds__((S / 4) * RPP) recrop_staged_kernel(SrcDev src, int64_t first, int64_t n,
+                                                                      uint8_t* __restrict__ out, const int64_t* __restrict__ n_dev, int64_t n_off) {
+    constexpr int UN = S / 4, THREADS = UN * RPP;
+    __shared__ int tabs[6 * S];
+    n = eff_count(n, n_dev, n_off);
+    __shared__ __align__(16) uint8_t rows[STAGE_BYTES + 16];
+    const int u = threadIdx.x % UN, r0 = threadIdx.x / UN;
+    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
+        const Crop c = make_crop(src, first + wrel);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + wrel * (int64_t)S * S * 3);
+        const bool empty = c.sw <= 0 || c.sh <= 0;
+        const bool same = c.sw == S && c.sh == S, half = c.sw == 2 * S && c.sh == 2 * S;
+        if (empty || same || half) {                            // uniform per window: zero / copy / INTER_AREA 2x2
+            for (int r = r0; r < S; r += RPP) {
+                uint32_t w[3] = {0u, 0u, 0u};
+                if (!empty) {
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int x = 4 * u + i;
+                        #pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            uint32_t v;
+                            if (same) v = c.base[(int64_t)r * c.pitch + x * 3 + ch];
+                            else {
+                                const uint8_t* p = c.base + (int64_t)(2 * r) * c.pitch + (2 * x) * 3 + ch;
+                                v = ((uint32_t)p[0] + p[3] + p[c.pitch] + p[c.pitch + 3] + 2u) >> 2;
+                            }
+                            const int b = i * 3 + ch;
+                            w[b >> 2] |= v << (8 * (b & 3));
+                        }
+                    }
+                }
+                uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
+                d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
+            }
+            continue;
+        }
+        __syncthreads();                                        // the previous window's tables and rows are free
+        for (int t = threadIdx.x; t < 2 * S; t += THREADS) {
+            int sidx, a0, a1;
+            if (t < S) { cv_tap(t, c.sw, S, true, sidx, a0, a1); tabs[t] = sidx; tabs[S + t] = a0; tabs[2 * S + t] = a1; }
+            else { const int d = t - S; cv_tap(d, c.sh, S, false, sidx, a0, a1); tabs[3 * S + d] = sidx; tabs[4 * S + d] = a0; tabs[5 * S + d] = a1; }
+        }
+        __syncthreads();
+        int xo[4], xlen[4], xa0[4], xa1[4];                     // byte offset of the first x tap, bytes to fetch, weights
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = 4 * u + i, sx = tabs[x];
+            xo[i] = sx * 3;
+            xlen[i] = sx + 1 <= c.sw - 1 ? 6 : 3;
+            xa0[i] = tabs[S + x]; xa1[i] = tabs[2 * S + x];
+        }
+        const int row_bytes = c.sw * 3;
+        // staged row: up to 15 bytes of alignment slack + the crop row + 12 bytes the last tap may read ahead
+        const int pitch = (row_bytes + 24 + 15) & ~15;
+        const int cap = STAGE_BYTES / pitch;                    // source rows the buffer holds
+        const bool staged = cap >= 4;
+        int nb = staged ? min(S, (cap - 2) / 2) : S;            // output rows per band
+        if (staged) { const int nbands = (S + nb - 1) / nb; nb = (S + nbands - 1) / nbands; }
+        for (int rb = 0; rb < S; rb += nb) {
+            const int re = min(S, rb + nb);
+            int ylo = 0; bool contig = false;
+            if (staged) {
+                ylo = min(max(tabs[3 * S + rb], 0), c.sh - 1);
+                const int yhi = min(max(tabs[3 * S + re - 1] + 1, 0), c.sh - 1);
+                contig = yhi - ylo + 1 <= cap;
+                const int nrows = contig ? yhi - ylo + 1 : 2 * (re - rb);
+                const int n16 = pitch >> 4;
+                if (rb > 0) __syncthreads();                    // the previous band has been consumed
+                for (int i = threadIdx.x; i < nrows * n16; i += THREADS) {
+                    const int rr = i / n16, k = i - rr * n16;
+                    const int y = contig ? ylo + rr : min(max(tabs[3 * S + rb + (rr >> 1)] + (rr & 1), 0), c.sh - 1);
+                    const uint8_t* g = c.base + (int64_t)y * c.pitch;
+                    const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+                    if (k * 16 < mis + row_bytes)               // this 16-byte word holds at least one byte of the row
+                        *reinterpret_cast<uint4*>(rows + rr * pitch + k * 16) = __ldg(reinterpret_cast<const uint4*>(g - mis) + k);
+                }
+                __syncthreads();
+            }
+            for (int r = rb + r0; r < re; r += RPP) {
+                const int sy = tabs[3 * S + r], b0 = tabs[4 * S + r], b1 = tabs[5 * S + r];
+                const int y0 = min(max(sy, 0), c.sh - 1), y1 = min(max(sy + 1, 0), c.sh - 1);
+                const uint8_t* p0 = c.base + (int64_t)y0 * c.pitch;
+                const uint8_t* p1 = c.base + (int64_t)y1 * c.pitch;
+                const uint8_t* s0 = rows + (contig ? y0 - ylo : 2 * (r - rb)) * pitch + (int)(reinterpret_cast<uintptr_t>(p0) & 15);
+                const uint8_t* s1 = rows + (contig ? y1 - ylo : 2 * (r - rb) + 1) * pitch + (int)(reinterpret_cast<uintptr_t>(p1) & 15);
+                uint32_t w[3] = {0u, 0u, 0u};
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t l0, h0, l1, h1;                    // the two taps of both rows: 6 adjacent bytes each
+                    if (staged) {
+                        lds_taps(s0, xo[i], l0, h0);
+                        lds_taps(s1, xo[i], l1, h1);
+                    } else {
+                        load_taps(p0 + xo[i], xlen[i], l0, h0);
+                        load_taps(p1 + xo[i], xlen[i], l1, h1);
+                    }
+                    // at the right border the bytes of the "second tap" are undefined, but its weight xa1 is 0
+                    #pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const int t00 = (int)((l0 >> (8 * ch)) & 255u), t10 = (int)((l1 >> (8 * ch)) & 255u);
+                        const int t01 = ch == 0 ? (int)(l0 >> 24) : (int)((h0 >> (8 * (ch - 1))) & 255u);
+                        const int t11 = ch == 0 ? (int)(l1 >> 24) : (int)((h1 >> (8 * (ch - 1))) & 255u);
+                        const int T0 = t00 * xa0[i] + t01 * xa1[i];
+                        const int T1 = t10 * xa0[i] + t11 * xa1[i];
+                        const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 255u;
+                        const int b = i * 3 + ch;
+                        w[b >> 2] |= v << (8 * (b & 3));
+                    }
+                }
+                uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
+                d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
+            }
+        }
+    }
+}
+
 constexpr int FEAT_THREADS = 256;
 
 // ------------------------------------------------------------------ feature kernel, generic sizes (smem pooling)
@@ -263,7 +400,9 @@ template <int OUT_SPLIT, int ST, int RT>
 __global__ void __launch_bounds__(FEAT_THREADS, 2)
 features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
                     const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
-                    float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                    float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                    const int64_t* __restrict__ n_dev, int64_t n_off) {
+    n = eff_count(n, n_dev, n_off);
     constexpr int C = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = ST ? ST : S_rt;
@@ -464,7 +603,9 @@ template <int OUT_SPLIT, int S>
 __global__ void __launch_bounds__(FEAT_THREADS, StreamCfg<S>::CTAS_PER_SM)
 features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
-                       float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                       float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                       const int64_t* __restrict__ n_dev, int64_t n_off) {
+    n = eff_count(n, n_dev, n_off);
     constexpr int NQ = StreamCfg<S>::NQ, WPW = StreamCfg<S>::WPW, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
     constexpr int VW = S * WPW;                                           // pixels of a warp row
     constexpr int C = 32, P = S + 2, TR = (VW + 15) / 16, NP = 2 * TR;   // NP pixels per thread and row
@@ -710,8 +851,9 @@ template <int OUT_SPLIT>
 __global__ void __launch_bounds__(FEAT_THREADS)
 features_general_kernel(SrcDev src, int64_t first, int64_t n, int S, GenNet net, float* __restrict__ scratch, int64_t max_act,
                         float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                        int64_t K) {
+                        int64_t K, const int64_t* __restrict__ n_dev, int64_t n_off) {
     extern __shared__ int gtabs[];
+    n = eff_count(n, n_dev, n_off);
     float* bufA = scratch + (int64_t)blockIdx.x * 2 * max_act;
     float* bufB = bufA + max_act;
     const int tid = threadIdx.x;
@@ -844,7 +986,8 @@ __global__ void __launch_bounds__(256) crop_area_kernel(SrcDev src, int64_t firs
     if ((threadIdx.x & 31) == 0 && a) atomicAdd(acc, a);
 }
 
-int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st) {
+int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st,
+                          const int64_t* n_dev, int64_t n_off) {
     if (n <= 0) return RODC_OK;
     const unsigned grid = (unsigned)(n < 148 * 64 ? n : 148 * 64);
     const bool rc_src = src.kind == RODC_SRC_RECROP;
@@ -855,15 +998,21 @@ int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size,
             crop_area_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(src, first, n, acc);
     }
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-    if (aligned && src.kind == RODC_SRC_RECROP && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out);
-    else if (aligned && src.kind == RODC_SRC_RECROP && size == 24) recrop_windows_kernel<24, 24><<<grid, 144, 0, st>>>(src, first, n, out);
-    else source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out);
+    // RODC_RECROP_SCATTER=1 selects the round-1 kernel (scattered tap loads): bit-identical output, kept as a cross-check
+    static int scatter = -1;
+    if (scatter < 0) { const char* e = getenv("RODC_RECROP_SCATTER"); scatter = (e && e[0] == '1') ? 1 : 0; }
+    if (aligned && rc_src && size == 48 && !scatter) recrop_staged_kernel<48, 16, 32 * 1024><<<grid, 192, 0, st>>>(src, first, n, out, n_dev, n_off);
+    else if (aligned && rc_src && size == 24 && !scatter) recrop_staged_kernel<24, 24, 24 * 1024><<<grid, 144, 0, st>>>(src, first, n, out, n_dev, n_off);
+    else if (aligned && rc_src && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out, n_dev, n_off);
+    else if (aligned && rc_src && size == 24) recrop_windows_kernel<24, 24><<<grid, 144, 0, st>>>(src, first, n, out, n_dev, n_off);
+    else source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out, n_dev, n_off);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
 
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
-                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch) {
+                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch,
+                    const int64_t* n_dev, int64_t n_off) {
     if (n <= 0) return RODC_OK;
     if (s->general) {
         RODC_CHECK_ARG(general_scratch != nullptr, "general-architecture stage needs activation scratch");
@@ -876,9 +1025,9 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         const size_t smem = (size_t)6 * s->in_size * sizeof(int);
         Prof prof(KC_FEAT, st, s->in_size, (double)n * ((double)s->in_size * s->in_size * 3 + 4.0 * (double)s->K), 0.0);
         if (out_f32) features_general_kernel<0><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
-                                                                                  1.f, out_f32, nullptr, nullptr, s->K);
+                                                                                  1.f, out_f32, nullptr, nullptr, s->K, n_dev, n_off);
         else features_general_kernel<1><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, s->in_size, net, general_scratch, s->max_act,
-                                                                          ldexpf(1.f, s->a_exp), nullptr, out_hi, out_lo, s->K);
+                                                                          ldexpf(1.f, s->a_exp), nullptr, out_hi, out_lo, s->K, n_dev, n_off);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
@@ -906,7 +1055,7 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
             const unsigned g3 = (unsigned)(n < 148 * StreamCfg<ST_>::CTAS_PER_SM ? n : 148 * StreamCfg<ST_>::CTAS_PER_SM);  \
             features_stream_kernel<SPLIT, ST_><<<g3, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,       \
                                                                                  ldexpf(1.f, s->a_exp - s->c_exp),          \
-                                                                                 ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo); \
+                                                                                 ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo, n_dev, n_off); \
         } while (0)
         if (out_f32) { if (S == 12) RODC_LAUNCH_FEAT3(0, 12); else if (S == 24) RODC_LAUNCH_FEAT3(0, 24); else RODC_LAUNCH_FEAT3(0, 48); }
         else { if (S == 12) RODC_LAUNCH_FEAT3(1, 12); else if (S == 24) RODC_LAUNCH_FEAT3(1, 24); else RODC_LAUNCH_FEAT3(1, 48); }
@@ -919,7 +1068,7 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         const size_t smem = feat2_smem_bytes(S, Rv);                                                                      \
         RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<SPLIT, ST_, RT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         features_mma_kernel<SPLIT, ST_, RT_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, Rv, s->conv_frag, s->conv_b, \
-                                                                                conv_scale, a_scale, out_f32, out_hi, out_lo); \
+                                                                                conv_scale, a_scale, out_f32, out_hi, out_lo, n_dev, n_off); \
     } while (0)
     { const int R = pick_rows2(S); if (out_f32) RODC_LAUNCH_FEAT(0, 0, 0, R); else RODC_LAUNCH_FEAT(1, 0, 0, R); }
 #undef RODC_LAUNCH_FEAT

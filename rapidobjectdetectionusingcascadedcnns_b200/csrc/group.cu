@@ -36,15 +36,18 @@ static GroupScratch carve(void* scratch, int64_t K, int F) {
 }
 
 // seg[f] = lower_bound(frame ids, f), f in [0, F]
-__global__ void group_segments_kernel(const int32_t* __restrict__ cand, int64_t K, int F, int32_t* __restrict__ seg) {
+__global__ void group_segments_kernel(const int32_t* __restrict__ cand, int64_t K, const int64_t* __restrict__ k_dev, int F,
+                                      int32_t* __restrict__ seg) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f > F) return;
+    K = eff_count(K, k_dev);
     int64_t lo = 0, hi = K;
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cand[mid * 5] < f) lo = mid + 1; else hi = mid; }
     seg[f] = (int32_t)lo;
 }
 
-__global__ void group_init_kernel(int32_t* __restrict__ parent, int32_t* __restrict__ sums, int64_t K) {
+__global__ void group_init_kernel(int32_t* __restrict__ parent, int32_t* __restrict__ sums, int64_t K, const int64_t* __restrict__ k_dev) {
+    K = eff_count(K, k_dev);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x) {
         parent[i] = (int32_t)i;
         #pragma unroll
@@ -95,10 +98,11 @@ __device__ __forceinline__ int4 load_xywh(const int32_t* cand, int64_t i) {
 // (A one-CTA-per-frame variant with the forest in shared memory was measured 10x slower: the scan,
 // not the atomics, is the cost, and it needs all SMs.)
 constexpr int GT = 256;
-__global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restrict__ cand, int64_t K,
+__global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restrict__ cand, int64_t K, const int64_t* __restrict__ k_dev,
                                                          const int32_t* __restrict__ seg, int32_t* __restrict__ parent, double eps) {
     __shared__ int4 tile[GT];
     __shared__ int tframe[GT];
+    K = eff_count(K, k_dev);
     // linear block id -> (bi, bj) with bj <= bi
     const long long b = blockIdx.x;
     long long bi = (long long)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(GT) group_union_kernel(const int32_t* __restri
     while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
     const long long bj = b - bi * (bi + 1) / 2;
     const int64_t i0 = bi * GT, j0 = bj * GT;
+    if (i0 >= K) return;                                    // grid sized for an upper bound of K
     // the i tile's first frame starts at seg[f_first]; j tiles that end before it hold other frames only
     const int f_first = cand[i0 * 5];
     if (j0 + GT <= seg[f_first]) return;
@@ -309,7 +314,9 @@ __global__ void group_emit_kernel(const int32_t* __restrict__ tmp, const int32_t
 }
 
 // min_neighbors <= 0: groupRectangles returns the input unchanged with weight 1
-__global__ void group_passthrough_kernel(const int32_t* __restrict__ cand, int64_t K, int32_t* __restrict__ out, int64_t* __restrict__ out_count) {
+__global__ void group_passthrough_kernel(const int32_t* __restrict__ cand, int64_t K, const int64_t* __restrict__ k_dev,
+                                         int32_t* __restrict__ out, int64_t* __restrict__ out_count) {
+    K = eff_count(K, k_dev);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < K; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t* c = cand + i * 5;
         int32_t* o = out + i * 6;
@@ -330,6 +337,11 @@ extern "C" int64_t rodc_group_scratch_bytes(int64_t k, int n_frames) {
 
 extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frames, int min_neighbors, double eps,
                                      int32_t* out, int64_t* out_count, void* scratch, void* stream) {
+    return rodc_group_rectangles_dyn(cand, k, nullptr, n_frames, min_neighbors, eps, out, out_count, scratch, stream);
+}
+
+extern "C" int rodc_group_rectangles_dyn(const int32_t* cand, int64_t k, const int64_t* k_dev, int n_frames, int min_neighbors,
+                                         double eps, int32_t* out, int64_t* out_count, void* scratch, void* stream) {
     RODC_CHECK_ARG(out_count != nullptr, "rodc_group_rectangles: out_count is NULL");
     RODC_CHECK_ARG(k >= 0 && k < (1ll << 30), "rodc_group_rectangles: bad k");
     cudaStream_t st = as_stream(stream);
@@ -338,22 +350,22 @@ extern "C" int rodc_group_rectangles(const int32_t* cand, int64_t k, int n_frame
     int blocks = (int)((k + 255) / 256);
     if (min_neighbors <= 0) {
         Prof prof(KC_GROUP, st, 0, 44.0 * (double)k, 0.0);
-        group_passthrough_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(cand, k, out, out_count);
+        group_passthrough_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(cand, k, k_dev, out, out_count);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
     GroupScratch g = carve(scratch, k, n_frames);
     // 20 K (candidates) + 24 K' (groups, K' <= K); the K^2 / 2 predicate evaluations are ALU work
     Prof prof(KC_GROUP, st, 0, 44.0 * (double)k, 0.0, 6);
-    group_segments_kernel<<<(n_frames + 1 + 255) / 256, 256, 0, st>>>(cand, k, n_frames, g.seg);
+    group_segments_kernel<<<(n_frames + 1 + 255) / 256, 256, 0, st>>>(cand, k, k_dev, n_frames, g.seg);
     RODC_LAUNCH_CHECK();
-    group_init_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(g.parent, g.sums, k);
+    group_init_kernel<<<blocks > 1184 ? 1184 : blocks, 256, 0, st>>>(g.parent, g.sums, k, k_dev);
     RODC_LAUNCH_CHECK();
     {
         const long long nb = (k + GT - 1) / GT;
         const long long tri = nb * (nb + 1) / 2;
         RODC_CHECK_ARG(tri < (1ll << 31), "rodc_group_rectangles: too many candidates for one launch (%lld)", (long long)k);
-        group_union_kernel<<<(unsigned)tri, GT, 0, st>>>(cand, k, g.seg, g.parent, eps);
+        group_union_kernel<<<(unsigned)tri, GT, 0, st>>>(cand, k, k_dev, g.seg, g.parent, eps);
     }
     RODC_LAUNCH_CHECK();
     group_finalize_kernel<<<n_frames, 1024, 0, st>>>(cand, g.seg, g.parent, g.cls, g.sums, g.rrect, g.tmp, g.fcount, min_neighbors, eps);

@@ -258,9 +258,17 @@ extern "C" int64_t rodc_stage_workspace_bytes(const rodc_stage* s, int64_t n, in
 extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
                                   float* bottleneck, int ld_bott, float* logits, float* probs,
                                   void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+    return rodc_stage_forward_dyn(s, src, first, n, nullptr, bottleneck, ld_bott, logits, probs, workspace, workspace_bytes,
+                                  impl, stream);
+}
+
+extern "C" int rodc_stage_forward_dyn(const rodc_stage* s, const rodc_window_source* src, int64_t first, int64_t n,
+                                      const int64_t* n_dev, float* bottleneck, int ld_bott, float* logits, float* probs,
+                                      void* workspace, int64_t workspace_bytes, int impl, void* stream) {
     RODC_CHECK_ARG(s && src && bottleneck && probs && workspace, "rodc_stage_forward: NULL argument");
     RODC_CHECK_ARG(ld_bott >= s->fc1_size + s->n_prev, "rodc_stage_forward: ld_bott %d < %d", ld_bott, s->fc1_size + s->n_prev);
     RODC_CHECK_ARG(impl == RODC_IMPL_TENSOR || impl == RODC_IMPL_SIMT, "rodc_stage_forward: unknown impl %d", impl);
+    RODC_CHECK_ARG(!n_dev || impl == RODC_IMPL_TENSOR, "rodc_stage_forward_dyn: device-side counts need the tensor fc1");
     if (n <= 0) return RODC_OK;
     SrcDev sd;
     int rc = resolve_source(src, s->in_size, &sd); if (rc) return rc;
@@ -274,6 +282,7 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         gscratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off);
         // the tensor fc1 needs fc1_size == 512 and K % 64 == 0; anything else runs the fp32 SIMT GEMM
         if (impl == RODC_IMPL_TENSOR && (s->fc1_size != 512 || s->K % 64 != 0)) impl = RODC_IMPL_SIMT;
+        RODC_CHECK_ARG(!n_dev || impl == RODC_IMPL_TENSOR, "rodc_stage_forward_dyn: this architecture runs the SIMT fc1, which takes no device-side count");
     }
     // The default-architecture feature kernels stream dense u8 windows (asynchronous prefetch); pyramid / re-crop /
     // gather sources are materialised per chunk first -- a window is 2 % of the bytes it expands to, and a
@@ -286,7 +295,7 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         SrcDev csrc = sd;
         int64_t cfirst = first + c0;
         if (materialise) {
-            if ((rc = launch_source_windows(sd, first + c0, m, s->in_size, dense_ws, st))) return rc;
+            if ((rc = launch_source_windows(sd, first + c0, m, s->in_size, dense_ws, st, n_dev, c0))) return rc;
             memset(&csrc, 0, sizeof(csrc));
             csrc.kind = RODC_SRC_DENSE; csrc.dense = dense_ws;
             cfirst = 0;
@@ -298,11 +307,11 @@ extern "C" int rodc_stage_forward(const rodc_stage* s, const rodc_window_source*
         } else {
             __half* hi = reinterpret_cast<__half*>(workspace);
             __half* lo = hi + m * s->K;
-            if ((rc = launch_features(s, csrc, cfirst, m, nullptr, hi, lo, st, gscratch))) return rc;
-            if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st))) return rc;
+            if ((rc = launch_features(s, csrc, cfirst, m, nullptr, hi, lo, st, gscratch, n_dev, c0))) return rc;
+            if ((rc = launch_fc1_tensor(s, hi, lo, m, bott, ld_bott, st, n_dev, c0))) return rc;
         }
     }
-    return launch_fc2_softmax(s, bottleneck, ld_bott, n, logits, probs, st);
+    return launch_fc2_softmax(s, bottleneck, ld_bott, n, logits, probs, st, n_dev);
 }
 
 extern "C" int rodc_stage_features_f32(const rodc_stage* s, const rodc_window_source* src, int64_t first,

@@ -48,16 +48,20 @@ struct SrcDev {
 int resolve_source(const rodc_window_source* src, int in_size, SrcDev* out);
 
 // features.cu
+// n_dev / n_off (optional): device-side count, effective n = clamp(*n_dev - n_off, 0, n) (common.cuh eff_count)
 int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64_t n,
-                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch = nullptr);
-int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st);
+                    float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t st, float* general_scratch = nullptr,
+                    const int64_t* n_dev = nullptr, int64_t n_off = 0);
+int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size, uint8_t* out, cudaStream_t st,
+                          const int64_t* n_dev = nullptr, int64_t n_off = 0);
 constexpr int GENERAL_CTAS = 296;     // persistent CTAs of the general-architecture feature kernel
 // fc.cu
 int launch_fc1_simt(const rodc_stage* s, const float* feat, int64_t m, float* bott, int ld_bott, cudaStream_t st);
-int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st);
+int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int64_t n, float* logits, float* probs, cudaStream_t st,
+                       const int64_t* n_dev = nullptr);
 // fc1_tc.cu
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
-                      float* bott, int ld_bott, cudaStream_t st);
+                      float* bott, int ld_bott, cudaStream_t st, const int64_t* m_dev = nullptr, int64_t m_off = 0);
 int prepare_fc1_split(rodc_stage* s, cudaStream_t st);
 
 }  // namespace rodc

@@ -275,6 +275,10 @@ class Stage:
                 C.c_void_p(f1.ctypes.data), C.c_void_p(f1b.ctypes.data), C.c_void_p(f2.ctypes.data),
                 C.c_void_p(f2b.ctypes.data), C.byref(h)), "rodc_stage_create_general")
         self._h = h
+        # the reference default (one 3x3x32 conv, 3x3/1 pool) runs the specialised kernels incl. the tensor fc1
+        self.is_default = (n_conv == 1 and int(chans[0]) == 32 and ksize == 3 and int(geo["conv_stride"]) == 1 and
+                           int(geo["pool_size"]) == 3 and int(geo["pool_stride"]) == 1 and self.in_size % 4 == 0 and
+                           self.fc1_size == 512)
 
     @property
     def handle(self):
@@ -319,8 +323,10 @@ def make_source(*, dense: Optional[torch.Tensor] = None, plan: Optional[Plan] = 
 
 def stage_forward(stage: Stage, src: WindowSource, first: int, n: int, bottleneck: torch.Tensor,
                   workspace: torch.Tensor, impl: int = IMPL_TENSOR,
-                  logits: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None):
-    """K2.  Writes ``bottleneck[:, :fc1]``; returns ``(logits [n,2], probs [n,2])``."""
+                  logits: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None,
+                  n_dev: Optional[torch.Tensor] = None):
+    """K2.  Writes ``bottleneck[:, :fc1]``; returns ``(logits [n,2], probs [n,2])``.  ``n_dev`` (device i64 [1]):
+    ``n`` is an upper bound and the kernels process ``min(n, n_dev)`` windows (``rodc_stage_forward_dyn``)."""
     _require_cuda(bottleneck, workspace)
     dev = bottleneck.device
     assert bottleneck.dtype == torch.float32 and bottleneck.stride(1) == 1 and bottleneck.shape[0] >= n
@@ -328,9 +334,9 @@ def stage_forward(stage: Stage, src: WindowSource, first: int, n: int, bottlenec
         logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
     if probs is None:
         probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    check(_lib.lib().rodc_stage_forward(stage.handle, C.byref(src), int(first), int(n), _ptr(bottleneck),
-                                        int(bottleneck.stride(0)), _ptr(logits), _ptr(probs), _ptr(workspace),
-                                        int(workspace.numel() * workspace.element_size()), int(impl), _stream()),
+    check(_lib.lib().rodc_stage_forward_dyn(stage.handle, C.byref(src), int(first), int(n), _ptr(n_dev), _ptr(bottleneck),
+                                            int(bottleneck.stride(0)), _ptr(logits), _ptr(probs), _ptr(workspace),
+                                            int(workspace.numel() * workspace.element_size()), int(impl), _stream()),
           "rodc_stage_forward")
     return logits, probs
 
@@ -356,8 +362,10 @@ CONF_LAST, CONF_AVG, CONF_MULT = 0, 1, 2
 def compact(probs: torch.Tensor, n: int, threshold: float, *, meta_in=None, meta_out=None,
             bott_in=None, width: int = 0, bott_out=None, col_off: int = 0,
             conf_acc=None, conf_out=None, conf_mode: int = CONF_LAST,
-            keep_idx: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None):
-    """K3.  Returns ``(keep_idx i32 [n], count i64 [1])`` -- both on the device (no sync)."""
+            keep_idx: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
+            n_dev: Optional[torch.Tensor] = None):
+    """K3.  Returns ``(keep_idx i32 [n], count i64 [1])`` -- both on the device (no sync).  ``n_dev``: device-side
+    count of the input rows (``n`` is then an upper bound)."""
     _require_cuda(probs)
     dev = probs.device
     if keep_idx is None:
@@ -366,7 +374,7 @@ def compact(probs: torch.Tensor, n: int, threshold: float, *, meta_in=None, meta
         count = torch.zeros((1,), dtype=torch.int64, device=dev)
     L = _lib.lib()
     scratch = torch.empty((int(L.rodc_compact_scratch_bytes(int(n))),), dtype=torch.uint8, device=dev)
-    check(L.rodc_compact(_ptr(probs), int(n), float(threshold), _ptr(meta_in), _ptr(meta_out),
+    check(L.rodc_compact_dyn(_ptr(probs), int(n), _ptr(n_dev), float(threshold), _ptr(meta_in), _ptr(meta_out),
                          _ptr(bott_in), int(bott_in.stride(0)) if bott_in is not None else 0, int(width),
                          _ptr(bott_out), int(bott_out.stride(0)) if bott_out is not None else 0, int(col_off),
                          _ptr(conf_acc), _ptr(conf_out), int(conf_mode), _ptr(keep_idx), _ptr(count), _ptr(scratch),
@@ -375,15 +383,17 @@ def compact(probs: torch.Tensor, n: int, threshold: float, *, meta_in=None, meta
 
 
 # --------------------------------------------------------------------------------- group rectangles
-def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: int = 1, eps: float = 0.2):
+def group_rectangles(cand: torch.Tensor, k: int, n_frames: int, min_neighbors: int = 1, eps: float = 0.2,
+                     k_dev: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None):
     """K5.  cand ``[K,5]`` i32 (frame, xmin,ymin,xmax,ymax) grouped by frame ->
     ``(out [K,6] i32 (frame,x,y,w,h,weight), count i64 [1])`` on the device."""
     _require_cuda(cand)
     dev = cand.device
     out = torch.empty((max(k, 1), 6), dtype=torch.int32, device=dev)
-    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    if count is None:
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
     L = _lib.lib()
     scratch = torch.empty((int(L.rodc_group_scratch_bytes(int(k), int(n_frames))),), dtype=torch.uint8, device=dev)
-    check(L.rodc_group_rectangles(_ptr(cand), int(k), int(n_frames), int(min_neighbors), float(eps), _ptr(out),
-                                  _ptr(count), _ptr(scratch), _stream()), "rodc_group_rectangles")
+    check(L.rodc_group_rectangles_dyn(_ptr(cand), int(k), _ptr(k_dev), int(n_frames), int(min_neighbors), float(eps), _ptr(out),
+                                      _ptr(count), _ptr(scratch), _stream()), "rodc_group_rectangles")
     return out, count

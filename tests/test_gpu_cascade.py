@@ -171,7 +171,8 @@ def test_error_conventions(pkg):
     ok = pkg.ArrayImageInfo(frames[0], "ok.png")
     pkg.cf.set("min_window_length", 0.2)
     res = app.run_inference_on_images([tiny, ok], merge=True)          # the tiny image is skipped, not fatal
-    assert res[0] == [] and isinstance(res[1], list)
+    from collections.abc import Sequence
+    assert res[0] == [] and isinstance(res[1], Sequence)      # a list, or the lazily materialised BoxList view of one
     assert app.run_inference_on_images([tiny, ok], merge=False)[0] == []
     with pytest.raises(ValueError):
         app.run_inference_on_images([tiny], merge=True)                # no window at all
@@ -308,3 +309,33 @@ def test_cascade_with_two_conv_layers(pkg):
             break
     if same:
         assert np.array_equal(g, ref)
+
+
+@pytest.mark.parametrize("name", ["cascade_small", "cascade_640x480", "cascade_conf_avg", "cascade_conf_mult"])
+@pytest.mark.parametrize("nms", ["NMS_OPENCV", "NMS_DISABLED"])
+def test_latency_path_equals_stage_by_stage_path(pkg, name, nms):
+    """The CUDA-graph path with device-side survivor counts (one host wait per call) returns exactly what the
+    stage-by-stage path (one count read per stage) returns: same kernels, same k order, same survivors."""
+    from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine
+    g, frames, weights, _ = case_inputs(name)
+    _set_cf(pkg, g["meta"]["cf"])
+    pkg.cf.set("nms", nms)
+    eng = CascadeEngine(weights)
+    for fr in frames:
+        batch = np.stack([fr, fr[::-1].copy()])                 # two frames of one shape
+        pkg.cf.set("latency_mode", pkg.cf.LATENCY_OFF)
+        a = eng.run_frames(batch)
+        pkg.cf.set("latency_mode", pkg.cf.LATENCY_ALWAYS)
+        b = eng.run_frames(batch)
+        c = eng.run_frames(batch)                               # replay of the captured graph
+        for r in (b, c):
+            assert (r.stage_in, r.stage_kept, r.n_windows) == (a.stage_in, a.stage_kept, a.n_windows)
+            assert np.array_equal(r.boxes, a.boxes) and np.array_equal(r.frame, a.frame)
+            assert np.array_equal(np.asarray(r.conf, np.float64), np.asarray(a.conf, np.float64))
+    # nothing survives stage 0: early stop, empty result, no stage after the empty one is reported
+    pkg.cf.set("foreground_confidence_threshold", 1.0)
+    e = eng.run_frames(np.stack([frames[0]]))
+    assert e.boxes.shape == (0, 4) and e.stage_kept == [0] and len(e.stage_in) == 1
+    pkg.cf.set("latency_mode", pkg.cf.LATENCY_OFF)
+    f = eng.run_frames(np.stack([frames[0]]))
+    assert (f.stage_in, f.stage_kept) == (e.stage_in, e.stage_kept)
