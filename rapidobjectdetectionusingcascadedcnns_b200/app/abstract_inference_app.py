@@ -64,6 +64,90 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
                                                                                traceback.format_exc()))
         return None
 
+    def _frame_size(self, img):
+        """(height, width) of an image WITHOUT decoding it when the object can tell (file header, array shape);
+        errors are swallowed like `:165-183` (the image yields [])."""
+        try:
+            h, w = getattr(img, "img_height_original", None), getattr(img, "img_width_original", None)
+            if h is None or w is None:
+                arr = img.raw_original(True)
+                h, w = arr.shape[0], arr.shape[1]
+            return int(h), int(w)
+        except FileNotFoundError:
+            log.log(" .. Skipped {}, because the file could not be found".format(getattr(img, "path_resized", img)))
+        except Exception:
+            log.log(" .. Skipped {}, because of an unexpected error:\n{}".format(getattr(img, "path_resized", img),
+                                                                               traceback.format_exc()))
+        return None
+
+    def _prepare_chunk(self, chunk, pool, slot: int):
+        """Decode the images of one chunk (in parallel when a pool is given), drop the ones that fail and upload the
+        rest on the CURRENT stream.  Returns ``(input indices, images, device payload, None)``."""
+        imgs = [i for _, i, _ in chunk]
+        frames = list(pool.map(self._load_frame, imgs)) if pool is not None else [self._load_frame(i) for i in imgs]
+        keep = [k for k, f in enumerate(frames) if f is not None]
+        if not keep:
+            return [], [], None, None
+        if slot:
+            self._engine.staging_slot = slot
+        payload = self._upload_frame_batch([frames[k] for k in keep])
+        return [chunk[k][0] for k in keep], [imgs[k] for k in keep], payload, None
+
+    def _chunk_feeder(self, chunks):
+        """Generator over prepared chunks: a feeder thread decodes (thread pool of ``cf decode_threads``) and
+        uploads (own CUDA stream, two alternating pinned staging buffers) up to two chunks ahead of the consumer."""
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        import torch
+        q = queue.Queue(maxsize=2)
+        device = self._engine.device
+        stop = threading.Event()
+
+        def work():
+            try:
+                torch.cuda.set_device(device)
+                side = torch.cuda.Stream(device=device)
+                n_thr = max(1, int(cf.get("decode_threads")))
+                with ThreadPoolExecutor(max_workers=n_thr) as pool:
+                    for k, chunk in enumerate(chunks):
+                        if stop.is_set():
+                            break
+                        with torch.cuda.stream(side):
+                            ids, infos, payload, _ = self._prepare_chunk(chunk, pool, 1 + (k & 1))
+                            ev = torch.cuda.Event()
+                            ev.record(side)
+                        q.put((ids, infos, payload, ev))
+            except BaseException as e:      # noqa: BLE001 -- handed to the consumer, which re-raises it
+                q.put(e)
+            q.put(None)
+
+        t = threading.Thread(target=work, name="rodc-chunk-feeder", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                yield item
+        finally:
+            stop.set()
+            while t.is_alive():             # unblock a feeder that waits on the bounded queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    t.join(timeout=0.05)
+
+    @staticmethod
+    def _wait_upload(event, payload):
+        """Make the compute stream wait for the feeder's copies and tell the caching allocator that the uploaded
+        buffers are now used on this stream."""
+        import torch
+        cur = torch.cuda.current_stream()
+        cur.wait_event(event)
+        kind, data = payload
+        (data if kind == "same" else data.flat).record_stream(cur)
+
     def run_inference_on_images(self, images: List, merge=True) -> List[List[LabeledBoundingBox]]:
         """`app/abstract_inference_app.py:38-156`.  The outer list has one inner list per input
         image (input order); each inner list holds the foreground boxes of that image."""
@@ -74,34 +158,54 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         if merge:
             timer_extracting = TimeWatcher("extract windows from all images and merge them")
             log.log(" -> extract")
-            usable = []                                       # (input index, image, frame) with at least one window
+            # 1. plan: image sizes from the file HEADERS (no decode), window counts from the planner
+            usable = []                                       # (input index, image, stage-0 windows)
             for idx, img in enumerate(images):
-                arr = self._load_frame(img)
-                if arr is None:
+                hw = self._frame_size(img)
+                if hw is None:
                     continue
                 try:
-                    n_win = self._windows_per_frame(arr.shape[1], arr.shape[0])      # raises if a window leaves its level
+                    n_win = self._windows_per_frame(hw[1], hw[0])      # raises if a window leaves its level
                     if n_win < 1:
                         raise ValueError("Could not extract any windows from the given image")
                 except ValueError as e:
                     log.log(" .. Skipped {}: {}".format(getattr(img, "path_resized", img), e))   # `:165-183`
                     continue
-                usable.append((idx, img, arr, n_win))
+                usable.append((idx, img, n_win))
             timer_extracting.stop()
             # cut into launches of at most cf['max_windows_per_launch'] stage-0 windows, input order kept
             budget = int(cf.get("max_windows_per_launch"))
             chunk, acc = [], 0
             chunks = []
             for item in usable:
-                if chunk and acc + item[3] > budget:
+                if chunk and acc + item[2] > budget:
                     chunks.append(chunk); chunk, acc = [], 0
-                chunk.append(item); acc += item[3]
+                chunk.append(item); acc += item[2]
             if chunk:
                 chunks.append(chunk)
-            for chunk in chunks:
-                per_frame = self._run_on_frame_batch([i for _, i, _, _ in chunk], [a for _, _, a, _ in chunk])
-                for (idx, _, _, _), boxes in zip(chunk, per_frame):
+            # 2. decode -> upload -> compute.  In-memory images of a single chunk go straight through; otherwise a
+            # feeder thread decodes chunk k + 1 with a thread pool and uploads it on its own stream while the
+            # GPU works on chunk k (the reference decodes every file once per pyramid scale on the calling
+            # thread, `data/image_info.py:228-240`).
+            in_memory = all(getattr(i, "_array", None) is not None for _, i, _ in usable)
+            n_done = 0
+            if len(chunks) == 1 and in_memory:
+                feed = [self._prepare_chunk(chunks[0], None, 0)]
+            else:
+                feed = self._chunk_feeder(chunks)
+            for item in feed:
+                if isinstance(item, BaseException):
+                    raise item
+                ids, infos, payload, event = item
+                if not ids:
+                    continue
+                if event is not None:
+                    self._wait_upload(event, payload)
+                per_frame = self._run_uploaded(infos, payload)
+                for idx, boxes in zip(ids, per_frame):
                     all_results[idx] = boxes
+                n_done += len(ids)
+            usable = [None] * n_done
             usable = len(usable)
             if usable == 0:
                 raise ValueError("Could not extract any windows from the given image")
@@ -134,4 +238,12 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
 
     @abc.abstractmethod
     def _windows_per_frame(self, w: int, h: int) -> int:
+        return
+
+    @abc.abstractmethod
+    def _upload_frame_batch(self, frames):
+        return
+
+    @abc.abstractmethod
+    def _run_uploaded(self, infos, payload) -> List[List[LabeledBoundingBox]]:
         return

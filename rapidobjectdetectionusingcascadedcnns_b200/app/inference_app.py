@@ -138,15 +138,27 @@ class InferenceApp(AbstractInferenceApp):
             out.append(LabeledBoundingBox.vertically_enlarge_bboxes(bl) if enlarge else bl)
         return out
 
+    def _upload_frame_batch(self, frames):
+        """Host frames -> device (on the current stream): one ``[n,H,W,3]`` tensor for one shape, a ``MixedFrames``
+        record for several.  Separate from the run so that the app can upload chunk k + 1 while chunk k computes."""
+        self._init_tf()
+        if len({f.shape for f in frames}) == 1:
+            return "same", self._engine.upload_host_frames(frames)
+        return "mixed", self._engine.upload_mixed(frames)
+
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
+        return self._run_uploaded(infos, self._upload_frame_batch(frames))
+
+    def _run_uploaded(self, infos, payload) -> List[List[LabeledBoundingBox]]:
         self._init_tf()
         self._update_input_dims()
-        if len({f.shape for f in frames}) == 1:
-            res = self._engine.run_frames(self._engine.upload_host_frames(frames))
+        kind, data = payload
+        if kind == "same":
+            res = self._engine.run_frames(data)
             self._log_stage_stats(res)
             return self._boxes_from_result(res, infos, len(infos))
         # several shapes: one merged set of stage launches (internal frame ids are grouped by shape)
-        res, order = self._engine.run_mixed(frames)
+        res, order = self._engine.run_mixed_device(data), data.order
         self._log_stage_stats(res)
         per_internal = self._boxes_from_result(res, [infos[i] for i in order], len(infos))
         out = [[] for _ in infos]

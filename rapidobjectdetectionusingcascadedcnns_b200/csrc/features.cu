@@ -239,140 +239,6 @@ __global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev sr
 }
 
 
-// K4, staged variant (default).  The scattered tap loads of recrop_windows_kernel kept the L1 request path busy
-// (ncu: l1tex 91 %, 5.7x more bytes through L1 than written, profiles/r1j_ncu_full_recrop48_byte_loads.txt).  Here a
-// CTA first copies the source rows a band of output rows needs into shared memory with coalesced 16-byte loads
-// (only 16-byte words that contain a byte of the crop row are touched, so nothing outside the frames buffer is
-// read), then resamples from shared memory with the same integer arithmetic.  A band takes either the contiguous
-// source-row range (down-scales below 2x: consecutive output rows share source rows, each is fetched once) or the
-// two rows of every output row (larger down-scales).  Crops too wide for the staging buffer fall back to the
-// scattered kernel's tap loads.
-__device__ __forceinline__ void lds_taps(const uint8_t* row, int off, uint32_t& lo, uint32_t& hi) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(row + (off & ~3));
-    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
-    const int sh = (off & 3) * 8;
-    lo = __funnelshift_r(w0, w1, sh);
-    hi = __funnelshift_r(w1, w2, sh);
-}
-
-template <int S, int RPP, int STAGE_BYTES>
-__global__ void __launch_bounds__((S / 4) * RPP) recrop_staged_kernel(SrcDev src, int64_t first, int64_t n,
-                                                                      uint8_t* __restrict__ out, const int64_t* __restrict__ n_dev, int64_t n_off) {
-    constexpr int UN = S / 4, THREADS = UN * RPP;
-    __shared__ int tabs[6 * S];
-    n = eff_count(n, n_dev, n_off);
-    __shared__ __align__(16) uint8_t rows[STAGE_BYTES + 16];
-    const int u = threadIdx.x % UN, r0 = threadIdx.x / UN;
-    for (int64_t wrel = blockIdx.x; wrel < n; wrel += gridDim.x) {
-        const Crop c = make_crop(src, first + wrel);
-        uint32_t* o = reinterpret_cast<uint32_t*>(out + wrel * (int64_t)S * S * 3);
-        const bool empty = c.sw <= 0 || c.sh <= 0;
-        const bool same = c.sw == S && c.sh == S, half = c.sw == 2 * S && c.sh == 2 * S;
-        if (empty || same || half) {                            // uniform per window: zero / copy / INTER_AREA 2x2
-            for (int r = r0; r < S; r += RPP) {
-                uint32_t w[3] = {0u, 0u, 0u};
-                if (!empty) {
-                    #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int x = 4 * u + i;
-                        #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            uint32_t v;
-                            if (same) v = c.base[(int64_t)r * c.pitch + x * 3 + ch];
-                            else {
-                                const uint8_t* p = c.base + (int64_t)(2 * r) * c.pitch + (2 * x) * 3 + ch;
-                                v = ((uint32_t)p[0] + p[3] + p[c.pitch] + p[c.pitch + 3] + 2u) >> 2;
-                            }
-                            const int b = i * 3 + ch;
-                            w[b >> 2] |= v << (8 * (b & 3));
-                        }
-                    }
-                }
-                uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
-                d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
-            }
-            continue;
-        }
-        __syncthreads();                                        // the previous window's tables and rows are free
-        for (int t = threadIdx.x; t < 2 * S; t += THREADS) {
-            int sidx, a0, a1;
-            if (t < S) { cv_tap(t, c.sw, S, true, sidx, a0, a1); tabs[t] = sidx; tabs[S + t] = a0; tabs[2 * S + t] = a1; }
-            else { const int d = t - S; cv_tap(d, c.sh, S, false, sidx, a0, a1); tabs[3 * S + d] = sidx; tabs[4 * S + d] = a0; tabs[5 * S + d] = a1; }
-        }
-        __syncthreads();
-        int xo[4], xlen[4], xa0[4], xa1[4];                     // byte offset of the first x tap, bytes to fetch, weights
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int x = 4 * u + i, sx = tabs[x];
-            xo[i] = sx * 3;
-            xlen[i] = sx + 1 <= c.sw - 1 ? 6 : 3;
-            xa0[i] = tabs[S + x]; xa1[i] = tabs[2 * S + x];
-        }
-        const int row_bytes = c.sw * 3;
-        // staged row: up to 15 bytes of alignment slack + the crop row + 12 bytes the last tap may read ahead
-        const int pitch = (row_bytes + 24 + 15) & ~15;
-        const int cap = STAGE_BYTES / pitch;                    // source rows the buffer holds
-        const bool staged = cap >= 4;
-        int nb = staged ? min(S, (cap - 2) / 2) : S;            // output rows per band
-        if (staged) { const int nbands = (S + nb - 1) / nb; nb = (S + nbands - 1) / nbands; }
-        for (int rb = 0; rb < S; rb += nb) {
-            const int re = min(S, rb + nb);
-            int ylo = 0; bool contig = false;
-            if (staged) {
-                ylo = min(max(tabs[3 * S + rb], 0), c.sh - 1);
-                const int yhi = min(max(tabs[3 * S + re - 1] + 1, 0), c.sh - 1);
-                contig = yhi - ylo + 1 <= cap;
-                const int nrows = contig ? yhi - ylo + 1 : 2 * (re - rb);
-                const int n16 = pitch >> 4;
-                if (rb > 0) __syncthreads();                    // the previous band has been consumed
-                for (int i = threadIdx.x; i < nrows * n16; i += THREADS) {
-                    const int rr = i / n16, k = i - rr * n16;
-                    const int y = contig ? ylo + rr : min(max(tabs[3 * S + rb + (rr >> 1)] + (rr & 1), 0), c.sh - 1);
-                    const uint8_t* g = c.base + (int64_t)y * c.pitch;
-                    const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);
-                    if (k * 16 < mis + row_bytes)               // this 16-byte word holds at least one byte of the row
-                        *reinterpret_cast<uint4*>(rows + rr * pitch + k * 16) = __ldg(reinterpret_cast<const uint4*>(g - mis) + k);
-                }
-                __syncthreads();
-            }
-            for (int r = rb + r0; r < re; r += RPP) {
-                const int sy = tabs[3 * S + r], b0 = tabs[4 * S + r], b1 = tabs[5 * S + r];
-                const int y0 = min(max(sy, 0), c.sh - 1), y1 = min(max(sy + 1, 0), c.sh - 1);
-                const uint8_t* p0 = c.base + (int64_t)y0 * c.pitch;
-                const uint8_t* p1 = c.base + (int64_t)y1 * c.pitch;
-                const uint8_t* s0 = rows + (contig ? y0 - ylo : 2 * (r - rb)) * pitch + (int)(reinterpret_cast<uintptr_t>(p0) & 15);
-                const uint8_t* s1 = rows + (contig ? y1 - ylo : 2 * (r - rb) + 1) * pitch + (int)(reinterpret_cast<uintptr_t>(p1) & 15);
-                uint32_t w[3] = {0u, 0u, 0u};
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t l0, h0, l1, h1;                    // the two taps of both rows: 6 adjacent bytes each
-                    if (staged) {
-                        lds_taps(s0, xo[i], l0, h0);
-                        lds_taps(s1, xo[i], l1, h1);
-                    } else {
-                        load_taps(p0 + xo[i], xlen[i], l0, h0);
-                        load_taps(p1 + xo[i], xlen[i], l1, h1);
-                    }
-                    // at the right border the bytes of the "second tap" are undefined, but its weight xa1 is 0
-                    #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const int t00 = (int)((l0 >> (8 * ch)) & 255u), t10 = (int)((l1 >> (8 * ch)) & 255u);
-                        const int t01 = ch == 0 ? (int)(l0 >> 24) : (int)((h0 >> (8 * (ch - 1))) & 255u);
-                        const int t11 = ch == 0 ? (int)(l1 >> 24) : (int)((h1 >> (8 * (ch - 1))) & 255u);
-                        const int T0 = t00 * xa0[i] + t01 * xa1[i];
-                        const int T1 = t10 * xa0[i] + t11 * xa1[i];
-                        const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 255u;
-                        const int b = i * 3 + ch;
-                        w[b >> 2] |= v << (8 * (b & 3));
-                    }
-                }
-                uint32_t* d = o + (r * S + 4 * u) * 3 / 4;
-                d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
-            }
-        }
-    }
-}
-
 constexpr int FEAT_THREADS = 256;
 
 // ------------------------------------------------------------------ feature kernel, generic sizes (smem pooling)
@@ -401,7 +267,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2)
 features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
                     const uint32_t* __restrict__ conv_frag, const float* __restrict__ conv_b, float conv_scale,
                     float a_scale, float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                    const int64_t* __restrict__ n_dev, int64_t n_off) {
+                    const int64_t* __restrict__ n_dev, int64_t n_off, int perm_side) {
     n = eff_count(n, n_dev, n_off);
     constexpr int C = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -551,7 +417,7 @@ features_mma_kernel(SrcDev src, int64_t first, int64_t n, int S_rt, int R_rt,
                             float2 m;
                             m.x = fmaxf(fmaxf(h[r][px].x, h[r + 1][px].x), h[r + 2][px].x);
                             m.y = fmaxf(fmaxf(h[r][px].y, h[r + 1][px].y), h[r + 2][px].y);
-                            const int64_t k = kbase + px * C;
+                            const int64_t k = OUT_SPLIT ? kperm(perm_side, kbase + px * C) : kbase + px * C;
                             if (OUT_SPLIT) {
                                 const float sx = m.x * a_scale, sy = m.y * a_scale;            // exact: power of two
                                 const __half2 h2 = __floats2half2_rn(sx, sy);
@@ -701,7 +567,14 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         // thread-constant output pointers (row offset added per row, pixel offsets are immediates)
         // ONE running output pointer per thread (element offset of output row ya - 2 + rr; the lo plane sits at
         // the kernel-uniform distance out_lo - out_hi), opaque so that it is carried instead of being rebuilt from %tid
-        int64_t oofs = wrel * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
+        // fp32 output (tests, SIMT fc1): the reference's NHWC order.  Split output: the permuted order of stage.cuh
+        // kperm -- row = [channel half][x'][16], x' = i G + group, so one store instruction of the warp (fixed pixel i,
+        // all lane groups) covers G x 32 contiguous bytes
+        constexpr int G = S / NP;                              // lane groups per window
+        constexpr int PIX = OUT_SPLIT ? G * 16 : C;            // element stride between a thread's pixels
+        int64_t oofs = OUT_SPLIT
+            ? wrel * (int64_t)S * S * C + (int64_t)(ya - 2) * S * C + cg * S * 16 + (xbase / NP) * 16 + 4 * t
+            : wrel * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
         asm volatile("" : "+l"(oofs));
         const int64_t lo_delta = OUT_SPLIT ? out_lo - out_hi : 0;
         const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + xbase * 4) + t;
@@ -791,10 +664,10 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
                             uint2 uh, ul;
                             uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
                             ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-                            *reinterpret_cast<uint2*>(out_hi + oofs + i * C) = uh;
-                            *reinterpret_cast<uint2*>(out_hi + oofs + lo_delta + i * C) = ul;
+                            *reinterpret_cast<uint2*>(out_hi + oofs + i * PIX) = uh;
+                            *reinterpret_cast<uint2*>(out_hi + oofs + lo_delta + i * PIX) = ul;
                         } else {
-                            *reinterpret_cast<float4*>(out_f32 + oofs + i * C) =
+                            *reinterpret_cast<float4*>(out_f32 + oofs + i * PIX) =
                                 make_float4(m[0] * inv_a_scale, m[1] * inv_a_scale, m[2] * inv_a_scale, m[3] * inv_a_scale);
                         }
                     }
@@ -998,12 +871,11 @@ int launch_source_windows(const SrcDev& src, int64_t first, int64_t n, int size,
             crop_area_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(src, first, n, acc);
     }
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-    // RODC_RECROP_SCATTER=1 selects the round-1 kernel (scattered tap loads): bit-identical output, kept as a cross-check
-    static int scatter = -1;
-    if (scatter < 0) { const char* e = getenv("RODC_RECROP_SCATTER"); scatter = (e && e[0] == '1') ? 1 : 0; }
-    if (aligned && rc_src && size == 48 && !scatter) recrop_staged_kernel<48, 16, 32 * 1024><<<grid, 192, 0, st>>>(src, first, n, out, n_dev, n_off);
-    else if (aligned && rc_src && size == 24 && !scatter) recrop_staged_kernel<24, 24, 24 * 1024><<<grid, 144, 0, st>>>(src, first, n, out, n_dev, n_off);
-    else if (aligned && rc_src && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out, n_dev, n_off);
+    // (A variant that first stages the source rows in shared memory with coalesced 16-byte loads was measured SLOWER:
+    // 254 vs 203 us per 18 944 windows at S = 48, 256 vs 128 us per 35 k at S = 24, profiles/r2b_ncu_small_kernels.json.
+    // With the aligned 8-byte tap loads this kernel is bound by its integer ALU work -- sm 84 %, l1tex 65 % -- not by
+    // the L1 request path any more, and the staging pass only adds instructions.)
+    if (aligned && rc_src && size == 48) recrop_windows_kernel<48, 16><<<grid, 192, 0, st>>>(src, first, n, out, n_dev, n_off);
     else if (aligned && rc_src && size == 24) recrop_windows_kernel<24, 24><<<grid, 144, 0, st>>>(src, first, n, out, n_dev, n_off);
     else source_windows_kernel<<<grid, 128, (size_t)6 * size * sizeof(int), st>>>(src, first, n, size, out, n_dev, n_off);
     RODC_LAUNCH_CHECK();
@@ -1068,7 +940,7 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
         const size_t smem = feat2_smem_bytes(S, Rv);                                                                      \
         RODC_CUDA(cudaFuncSetAttribute(features_mma_kernel<SPLIT, ST_, RT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         features_mma_kernel<SPLIT, ST_, RT_><<<grid, FEAT_THREADS, smem, st>>>(src, first, n, S, Rv, s->conv_frag, s->conv_b, \
-                                                                                conv_scale, a_scale, out_f32, out_hi, out_lo, n_dev, n_off); \
+                                                                                conv_scale, a_scale, out_f32, out_hi, out_lo, n_dev, n_off, s->kperm_side); \
     } while (0)
     { const int R = pick_rows2(S); if (out_f32) RODC_LAUNCH_FEAT(0, 0, 0, R); else RODC_LAUNCH_FEAT(1, 0, 0, R); }
 #undef RODC_LAUNCH_FEAT

@@ -22,7 +22,7 @@ namespace rodc {
 // W[K, N] fp32 (N contiguous) -> hi/lo fp16 planes [N, K] (K contiguous), W * 2^w_exp = hi + lo.
 // 32x32 smem transpose so both the read and the writes are coalesced.
 __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ W, int64_t K, int N, float scale,
-                                                              __half* __restrict__ hi, __half* __restrict__ lo) {
+                                                              __half* __restrict__ hi, __half* __restrict__ lo, int perm_side) {
     __shared__ float tile[32][33];
     const int64_t k0 = (int64_t)blockIdx.x * 32;
     const int n0 = blockIdx.y * 32;
@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
         if (n < N && k < K) {
             const float v = tile[tx][r] * scale;
             const __half h = __float2half_rn(v);
-            hi[(int64_t)n * K + k] = h;
-            lo[(int64_t)n * K + k] = __float2half_rn(v - __half2float(h));
+            const int64_t kp = kperm(perm_side, k);             // the order the feature kernels write A in
+            hi[(int64_t)n * K + kp] = h;
+            lo[(int64_t)n * K + kp] = __float2half_rn(v - __half2float(h));
         }
     }
 }
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
 int prepare_fc1_split(rodc_stage* s, cudaStream_t st) {
     dim3 grid((unsigned)((s->K + 31) / 32), (unsigned)((s->fc1_size + 31) / 32));
     Prof prof(KC_MISC, st, 0, 8.0 * (double)s->K * s->fc1_size, 0.0);
-    split_transpose_kernel<<<grid, 256, 0, st>>>(s->fc1_w, s->K, s->fc1_size, ldexpf(1.f, s->w_exp), s->fc1_hi, s->fc1_lo);
+    split_transpose_kernel<<<grid, 256, 0, st>>>(s->fc1_w, s->K, s->fc1_size, ldexpf(1.f, s->w_exp), s->fc1_hi, s->fc1_lo,
+                                                 s->kperm_side);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }
@@ -83,6 +85,7 @@ extern "C" int rodc_stage_create(int in_size, int conv_channels, int fc1_size, i
     if (!s) { set_error("out of host memory"); return RODC_ERR_NOMEM; }
     s->in_size = in_size; s->channels = conv_channels; s->fc1_size = fc1_size; s->n_prev = n_prev;
     s->K = (int64_t)in_size * in_size * conv_channels;
+    s->kperm_side = (in_size == 12 || in_size == 24 || in_size == 48) ? in_size : 0;
     int rc = cudaGetDevice(&s->device) == cudaSuccess ? RODC_OK : RODC_ERR_CUDA;
     if (rc) { set_error("no CUDA device"); delete s; return rc; }
     const size_t nconv = (size_t)27 * conv_channels, nfc1 = (size_t)s->K * fc1_size, nfc2 = (size_t)(fc1_size + n_prev) * 2;

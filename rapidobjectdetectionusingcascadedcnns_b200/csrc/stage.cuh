@@ -21,6 +21,9 @@ struct rodc_stage {
     __half* fc1_lo = nullptr;
     uint32_t* conv_frag = nullptr;  // mma.sync B fragments of the conv: [3 ky][4 nt][hi,lo][32 lanes][2] half2
     uint32_t* conv_frag_perm = nullptr;   // same, n-tile columns permuted so a thread owns 4 adjacent channels (v3)
+    // K order of the SPLIT fc1 operand (A planes written by the feature kernels, B planes fc1_hi / fc1_lo): in_size when
+    // the streaming feature kernel's store-friendly order is in use (see kperm below), 0 = the reference's NHWC order
+    int kperm_side = 0;
     int c_exp = 0;              // conv weights are scaled by 2^c_exp before the fp16 split
     int a_exp = 0;              // features are scaled by 2^a_exp before the fp16 split
     int w_exp = 0;              // weights  are scaled by 2^w_exp before the fp16 split
@@ -35,6 +38,23 @@ struct rodc_stage {
 };
 
 namespace rodc {
+
+// K order of the split fc1 operand for the streaming feature kernels (S = 12 / 24 / 48).  fc1 is a sum over K, so the
+// order is free as long as the A planes and the prepared weights agree.  The reference's NHWC flatten order
+// (k = (y S + x) 32 + c) makes a warp of the feature kernel scatter every store instruction over eight 128-byte lines
+// (a warp owns 16 of a pixel's 32 channels and its eight lane groups own pixels six apart): the stores alone were
+// 70 % of that kernel's L1 wavefronts (profiles/r2a_ncu_kernels.json: l1tex 79 %, the top unit).  In the permuted order
+// a row is stored as [channel half][x'][16 channels] with x' = (x mod NP) G + x / NP (NP pixels per thread, G lane
+// groups per window), so the eight lane groups of one store instruction write 8 x 32 = 256 contiguous bytes.
+__host__ __device__ inline int64_t kperm(int S, int64_t k) {
+    if (S != 12 && S != 24 && S != 48) return k;
+    const int NPX = S == 12 ? 2 : 6, G = S / NPX;
+    const int c = (int)(k & 31);
+    const int64_t px = k >> 5;
+    const int x = (int)(px % S);
+    const int64_t y = px / S;
+    return (((y * 2 + (c >> 4)) * S) + (x % NPX) * G + x / NPX) * 16 + (c & 15);
+}
 
 // Resolved window source passed by value to the feature kernel.
 struct SrcDev {

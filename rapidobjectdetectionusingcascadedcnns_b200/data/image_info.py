@@ -71,6 +71,7 @@ class FileImageInfo(ArrayImageInfo):
         self._key = path_original
         self._dataset_key = dataset_key
         self._array = None
+        self._wh = None
 
     def raw_original(self, cache=False) -> np.ndarray:
         if self._array is None:
@@ -81,13 +82,23 @@ class FileImageInfo(ArrayImageInfo):
             self._array = np.ascontiguousarray(arr)
         return self._array
 
+    def _size(self):
+        """(width, height) from the file header only: planning the launch chunks must not cost a decode."""
+        if self._array is not None:
+            return int(self._array.shape[1]), int(self._array.shape[0])
+        if getattr(self, "_wh", None) is None:
+            from PIL import Image
+            with Image.open(self._path) as im:
+                self._wh = (int(im.size[0]), int(im.size[1]))
+        return self._wh
+
     @property
     def img_height_original(self) -> int:
-        return int(self.raw_original(True).shape[0])
+        return self._size()[1]
 
     @property
     def img_width_original(self) -> int:
-        return int(self.raw_original(True).shape[1])
+        return self._size()[0]
 
     def clear_raw_img_cache(self):
         self._array = None

@@ -75,6 +75,8 @@ class CascadeEngine:
         self._plans: Dict[Tuple, native.Plan] = {}
         self._scaled_plans: Dict[Tuple, native.Plan] = {}
         self._ws: Optional[torch.Tensor] = None
+        import threading
+        self._tls = threading.local()
         self._validate_chain()
 
     # ------------------------------------------------------------------ helpers
@@ -180,21 +182,31 @@ class CascadeEngine:
     def _pinned_stage(self, nbytes: int) -> torch.Tensor:
         """The pinned staging buffer (grown on demand).  Before it is handed out again the H2D copies issued from
         it by the previous user must have finished: they are asynchronous and the host is about to overwrite it."""
-        ev = getattr(self, "_pinned_busy", None)
-        if ev is not None:
-            ev.synchronize()
-            self._pinned_busy = None
-        buf = getattr(self, "_pinned", None)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
-            self._pinned = buf
-        return buf
+        slots = self.__dict__.setdefault("_stage_slots", {})
+        slot = slots.setdefault(self.staging_slot, {"buf": None, "busy": None})
+        if slot["busy"] is not None:
+            slot["busy"].synchronize()
+            slot["busy"] = None
+        if slot["buf"] is None or slot["buf"].numel() < nbytes:
+            slot["buf"] = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+        return slot["buf"]
 
     def _pinned_issued(self):
         """Call after the last asynchronous copy out of the staging buffer has been enqueued."""
         ev = torch.cuda.Event()
         ev.record()
-        self._pinned_busy = ev
+        self._stage_slots[self.staging_slot]["busy"] = ev
+
+    @property
+    def staging_slot(self) -> int:
+        """Which pinned staging buffer the calling thread uses (thread local; the upload thread of the app's
+        decode -> upload pipeline alternates between two of its own so that the upload of chunk k + 1 can be
+        staged while chunk k's copy is still in flight)."""
+        return getattr(self._tls, "slot", 0)
+
+    @staging_slot.setter
+    def staging_slot(self, v: int):
+        self._tls.slot = int(v)
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
@@ -286,12 +298,7 @@ class CascadeEngine:
                 if mode_key != cf.FINAL_CONFIDENCE_CALCULATION_LAST_STEP:
                     conf_acc = conf_out
             elif last:
-                final_conf = conf_out[:kept]
-                if mode_key == cf.FINAL_CONFIDENCE_CALCULATION_AVG:
-                    final_conf = final_conf / np.float32(n_st)
-                elif mode_key == cf.FINAL_CONFIDENCE_CALCULATION_MULT:
-                    final_conf = torch.clamp(final_conf, min=np.float32(cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT))
-                res = self._finish(res, meta, final_conf, kept, n_frames)
+                res = self._finish(res, meta, conf_out[:kept], kept, n_frames)
         res.trace = trace
         return res
 
@@ -310,8 +317,20 @@ class CascadeEngine:
             rows = meta[:k].cpu().numpy()
             res.frame = rows[:, 0].copy()
             res.boxes = rows[:, 1:5].astype(np.int32)
-            res.conf = conf.cpu().numpy()
+            res.conf = self._finalise_confidences(conf.cpu().numpy())
         return res
+
+    def _finalise_confidences(self, c: np.ndarray) -> np.ndarray:
+        """`app/inference_cascade_app.py:322-327` in the reference's own arithmetic: a float32 NumPy array divided in
+        place by the number of nets (a true IEEE division -- a device-side ``tensor / scalar`` multiplies by the
+        reciprocal and can differ in the last bit) or floored at the MULT minimum."""
+        mode_key = cf.get("final_confidence_calculation")
+        c = np.array(c, np.float32)
+        if mode_key == cf.FINAL_CONFIDENCE_CALCULATION_AVG:
+            c /= len(self.stages)
+        elif mode_key == cf.FINAL_CONFIDENCE_CALCULATION_MULT:
+            c[c < cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT] = cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT
+        return c
 
     # ------------------------------------------------------------------ public entry points
     def stage_host_frames(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
@@ -469,13 +488,7 @@ class CascadeEngine:
             m = meta[:k_last]
             res.frame = m[:, 0].copy()
             res.boxes = m[:, 1:5].astype(np.int32)
-            c = conf[:k_last].copy()
-            mode_key = cf.get("final_confidence_calculation")
-            if mode_key == cf.FINAL_CONFIDENCE_CALCULATION_AVG:
-                c = c / np.float32(n_st)
-            elif mode_key == cf.FINAL_CONFIDENCE_CALCULATION_MULT:
-                c = np.maximum(c, np.float32(cf.MIN_SCORE_FOR_FINAL_CONFIDENCE_CALCULATION_MULT))
-            res.conf = c
+            res.conf = self._finalise_confidences(conf[:k_last])
         return res
 
     def _cf_signature(self):

@@ -216,3 +216,49 @@ def test_run_sharded_over_nccl_equals_single_rank():
     for rank, same, n in got:
         assert same is True, (rank, n)
         assert n > 0
+
+
+def test_decode_upload_pipeline_from_files(pkg, tmp_path):
+    """files are decoded ONCE by a thread pool and uploaded on a side stream while the previous
+    chunk computes.  Results from files (PNG, lossless) == results from the same frames in memory, for one chunk
+    and for many small chunks; an unreadable file yields [] without disturbing its neighbours
+    (`app/abstract_inference_app.py:165-183`)."""
+    from PIL import Image
+    g, frames, weights, _ = case_inputs("cascade_small_reject")
+    _set_cf(pkg, g["meta"]["cf"])
+    frames = list(frames) + [frames[0][:, ::-1].copy(), frames[1][::-1].copy()]
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / ("img_%d.png" % i))
+        Image.fromarray(f).save(p)
+        paths.append(p)
+    bad = str(tmp_path / "broken.png")
+    with open(bad, "wb") as fh:
+        fh.write(b"this is not a png")
+    missing = str(tmp_path / "missing.png")
+    app = pkg.InferenceCascadeApp("files", stage_models=[pkg.StageModel(w) for w in weights])
+    ref = _rows(app.run_inference_on_images([pkg.ArrayImageInfo(f, "a_%d.png" % i) for i, f in enumerate(frames)], merge=True))
+    assert ref.shape[0] > 0
+
+    def file_infos():
+        return [pkg.FileImageInfo(p) for p in paths]
+    got = _rows(app.run_inference_on_images(file_infos(), merge=True))
+    np.testing.assert_array_equal(got, ref)
+    # header-only planning: sizes are known before any pixel is decoded
+    fi = pkg.FileImageInfo(paths[0])
+    assert (fi.img_height_original, fi.img_width_original) == frames[0].shape[:2] and fi._array is None
+    # many small chunks -> the feeder thread runs ahead of the GPU; same boxes
+    pkg.cf.set("max_windows_per_launch", 600)
+    got2 = _rows(app.run_inference_on_images(file_infos(), merge=True))
+    np.testing.assert_array_equal(got2, ref)
+    # unreadable / missing files in the middle: [] for them, the rest unchanged
+    infos = file_infos()
+    infos.insert(2, pkg.FileImageInfo(bad))
+    infos.insert(4, pkg.FileImageInfo(missing))
+    res = app.run_inference_on_images(infos, merge=True)
+    assert res[2] == [] and res[4] == []
+    rest = [r for k, r in enumerate(res) if k not in (2, 4)]
+    np.testing.assert_array_equal(_rows(rest), ref)
+    pkg.cf.set("max_windows_per_launch", 1 << 18)
+    with pytest.raises(ValueError):
+        app.run_inference_on_images([pkg.FileImageInfo(bad), pkg.FileImageInfo(missing)], merge=True)
