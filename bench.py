@@ -418,7 +418,17 @@ def main():
             eng.run_frames(one)
         ms_one = timed(lambda: eng.run_frames(one), 10) / 10.0
         single = {"ms_per_frame": ms_one, "frames_per_s": 1000.0 / ms_one,
-                  "note": "one 640x480 frame per call (no batching): 5061 windows fill < 1 wave of 148 SMs"}
+                  "note": "BASELINE config 2 as written: one 640x480 frame per call (no batching), the bench's uncalibrated "
+                          "weights (4434 of 5061 windows reach the 48-px stage); one CUDA graph, one host wait per call"}
+        # the same frame through a cascade with realistic rejection (config 3's offsets): what an un-batched call costs
+        # when the cascade does what it is built for
+        eng_c = CascadeEngine(cascade_weights(3), device=local_rank)
+        for _ in range(3):
+            r_c = eng_c.run_frames(one)
+        ms_cal = timed(lambda: eng_c.run_frames(one), 10) / 10.0
+        single["calibrated"] = {"ms_per_frame": ms_cal, "frames_per_s": 1000.0 / ms_cal, "stage_kept": r_c.stage_kept,
+                                "note": "same frame, fc2.b[1] offsets [-40, -85, -24]"}
+        del eng_c
 
     if rank == 0:
         frames_step = total_frames if conf["scaling"] == "strong" else B * world
