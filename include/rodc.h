@@ -71,6 +71,14 @@ int64_t rodc_plan_scratch_bytes(const rodc_plan* p);   /* horizontal-pass rows o
 int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, uint8_t* pyramid,
                  uint8_t* scratch, void* stream);
 
+/* Host frames -> one flat device buffer: one cudaMemcpyAsync per frame (frame i: nbytes[i] bytes from
+ * host_frames[i] to dev_base + dev_off[i]) issued from ONE call, so that a batch of hundreds of small frames costs
+ * one trip through the binding instead of one per frame.  The copies are asynchronous only for page-locked host
+ * memory (cudaHostAlloc / cudaHostRegister); the reference has no counterpart (it keeps images on the host,
+ * data/image_info.py:197-213). */
+int rodc_upload_frames(const void* const* host_frames, const int64_t* nbytes, const int64_t* dev_off, int n,
+                       uint8_t* dev_base, void* stream);
+
 /* Raw stage-0 windows, order frame -> level -> x -> y (data/rectangles.py:291,409):
  *   windows [n_frames * n_windows, win, win, 3] u8 */
 int rodc_extract_windows(rodc_plan* p, const uint8_t* pyramid, int n_frames, uint8_t* windows,

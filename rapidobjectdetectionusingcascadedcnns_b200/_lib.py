@@ -67,6 +67,7 @@ SIGNATURES = {
     "rodc_stage_workspace_bytes": (C.c_int64, [vp, C.c_int64, C.c_int]),
     "rodc_stage_forward": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, C.c_int, vp, vp,
                                      vp, C.c_int64, C.c_int, vp]),
+    "rodc_upload_frames": (C.c_int, [C.POINTER(vp), c_i64p, c_i64p, C.c_int, vp, vp]),
     "rodc_stage_forward_dyn": (C.c_int, [vp, C.POINTER(WindowSource), C.c_int64, C.c_int64, vp, vp, C.c_int, vp, vp,
                                          vp, C.c_int64, C.c_int, vp]),
     "rodc_compact_dyn": (C.c_int, [vp, C.c_int64, vp, C.c_double, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,

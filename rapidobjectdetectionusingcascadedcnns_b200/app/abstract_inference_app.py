@@ -84,7 +84,8 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         """Decode the images of one chunk (in parallel when a pool is given), drop the ones that fail and upload the
         rest on the CURRENT stream.  Returns ``(input indices, images, device payload, None)``."""
         imgs = [i for _, i, _ in chunk]
-        frames = list(pool.map(self._load_frame, imgs)) if pool is not None else [self._load_frame(i) for i in imgs]
+        decode = pool is not None and any(getattr(i, "_array", None) is None for i in imgs)     # else: nothing to decode
+        frames = list(pool.map(self._load_frame, imgs)) if decode else [self._load_frame(i) for i in imgs]
         keep = [k for k, f in enumerate(frames) if f is not None]
         if not keep:
             return [], [], None, None
@@ -148,11 +149,20 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         kind, data = payload
         (data if kind == "same" else data.flat).record_stream(cur)
 
-    def run_inference_on_images(self, images: List, merge=True) -> List[List[LabeledBoundingBox]]:
+    def run_inference_rows(self, images: List) -> np.ndarray:
+        """``run_inference_on_images(images, merge=True)`` with the detections as ONE array ``[K,6]`` of rows
+        ``(input index, xmin, ymin, xmax, ymax, confidence)`` sorted by input index (per-image order kept): what
+        `dist.run_sharded` exchanges.  No box object and no per-image list is created."""
+        return self.run_inference_on_images(images, merge=True, _as_rows=True)
+
+    def run_inference_on_images(self, images: List, merge=True, _as_rows: bool = False) -> List[List[LabeledBoundingBox]]:
         """`app/abstract_inference_app.py:38-156`.  The outer list has one inner list per input
         image (input order); each inner list holds the foreground boxes of that image."""
         self._init_tf()
+        if _as_rows and not merge:
+            raise ValueError("row output is a merge-mode feature")
         all_results = [[] for _ in images]
+        row_parts = []
         timer_multiple = TimeWatcher("inference_img_multiple: {} imgs".format(len(images)))
         timer_extracting = None
         if merge:
@@ -201,9 +211,13 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
                     continue
                 if event is not None:
                     self._wait_upload(event, payload)
-                per_frame = self._run_uploaded(infos, payload)
-                for idx, boxes in zip(ids, per_frame):
-                    all_results[idx] = boxes
+                if _as_rows:
+                    local, rows = self._run_uploaded(infos, payload, as_rows=True)
+                    row_parts.append(np.column_stack([np.asarray(ids, np.float64)[local], rows]).reshape(-1, 6))
+                else:
+                    per_frame = self._run_uploaded(infos, payload)
+                    for idx, boxes in zip(ids, per_frame):
+                        all_results[idx] = boxes
                 n_done += len(ids)
             usable = [None] * n_done
             usable = len(usable)
@@ -234,6 +248,9 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         t_all = timer_multiple.elapsed_seconds
         log.log("Runtime inference including window extraction: {} images in {} (avg: {}).".format(
             len(images), TimeWatcher.seconds_to_str(t_all), TimeWatcher.seconds_to_str(t_all / n)))
+        if _as_rows:
+            rows = np.concatenate(row_parts) if row_parts else np.zeros((0, 6), np.float64)
+            return rows[np.argsort(rows[:, 0], kind="stable")]
         return all_results
 
     @abc.abstractmethod

@@ -116,6 +116,17 @@ class InferenceApp(AbstractInferenceApp):
 
     # ------------------------------------------------------------------ results
     @staticmethod
+    def _rows_from_result(res) -> np.ndarray:
+        """``[K,5]`` float64 rows (xmin, ymin, xmax, ymax, confidence) incl. the optional vertical enlargement
+        (`data/rectangles.py:185-220` defaults: ``ymin' = max(ymin - 0.2 height, 0)``)."""
+        rows = np.empty((res.boxes.shape[0], 5), np.float64)
+        rows[:, :4] = res.boxes
+        rows[:, 4] = res.conf
+        if cf.get("vertically_enlarge_bboxes") and rows.shape[0]:
+            rows[:, 1] = np.maximum(rows[:, 1] - 0.2 * (rows[:, 3] - rows[:, 1]), 0)
+        return rows
+
+    @staticmethod
     def _boxes_from_result(res, infos, n_frames: int, flat: bool = False):
         """Per-frame ``BoxList`` views of the result arrays (objects are created on first use).  ``flat=True``
         returns ONE list over all frames in result order (``run_inference_on_windows`` without NMS)."""
@@ -149,17 +160,23 @@ class InferenceApp(AbstractInferenceApp):
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
         return self._run_uploaded(infos, self._upload_frame_batch(frames))
 
-    def _run_uploaded(self, infos, payload) -> List[List[LabeledBoundingBox]]:
+    def _run_uploaded(self, infos, payload, as_rows: bool = False):
+        """Run one uploaded chunk.  Returns one result list per frame, or with ``as_rows`` the arrays
+        ``(frame index inside the chunk [K], rows [K,5] = xmin, ymin, xmax, ymax, confidence)`` without any object."""
         self._init_tf()
         self._update_input_dims()
         kind, data = payload
         if kind == "same":
             res = self._engine.run_frames(data)
             self._log_stage_stats(res)
+            if as_rows:
+                return np.asarray(res.frame, np.int64), self._rows_from_result(res)
             return self._boxes_from_result(res, infos, len(infos))
         # several shapes: one merged set of stage launches (internal frame ids are grouped by shape)
         res, order = self._engine.run_mixed_device(data), data.order
         self._log_stage_stats(res)
+        if as_rows:
+            return np.asarray(order, np.int64)[np.asarray(res.frame, np.int64)], self._rows_from_result(res)
         per_internal = self._boxes_from_result(res, [infos[i] for i in order], len(infos))
         out = [[] for _ in infos]
         for internal, i in enumerate(order):

@@ -287,6 +287,17 @@ extern "C" int rodc_window_levels(rodc_plan* p, int n_frames, int slot_base, int
     return RODC_OK;
 }
 
+extern "C" int rodc_upload_frames(const void* const* host_frames, const int64_t* nbytes, const int64_t* dev_off, int n,
+                                  uint8_t* dev_base, void* stream) {
+    RODC_CHECK_ARG(host_frames && nbytes && dev_off && dev_base && n >= 0, "rodc_upload_frames: bad argument");
+    cudaStream_t st = as_stream(stream);
+    for (int i = 0; i < n; ++i) {
+        RODC_CHECK_ARG(host_frames[i] && nbytes[i] >= 0 && dev_off[i] >= 0, "rodc_upload_frames: bad frame %d", i);
+        RODC_CUDA(cudaMemcpyAsync(dev_base + dev_off[i], host_frames[i], (size_t)nbytes[i], cudaMemcpyHostToDevice, st));
+    }
+    return RODC_OK;
+}
+
 extern "C" int rodc_select_rows(const void* in, const int32_t* idx, int64_t n, int row_bytes, void* out, void* stream) {
     RODC_CHECK_ARG(in && idx && out, "rodc_select_rows: NULL argument");
     RODC_CHECK_ARG(row_bytes > 0 && (row_bytes & 3) == 0, "rodc_select_rows: row_bytes must be a positive multiple of 4 (got %d)", row_bytes);

@@ -10,6 +10,11 @@ import os
 import numpy as np
 
 
+# data pointers of the frames that ``ArrayImageInfo(..., pin=True)`` placed in page-locked memory (a set lookup is
+# cheaper than asking the driver about every frame of every batch)
+PINNED_FRAME_PTRS = set()
+
+
 class ArrayImageInfo:
     """An in-memory ``[H,W,3]`` uint8 frame (synthetic frames, video streams)."""
 
@@ -24,10 +29,16 @@ class ArrayImageInfo:
             self._pinned = torch.empty(a.shape, dtype=torch.uint8).pin_memory()
             self._array = self._pinned.numpy()
             self._array[...] = a
+            PINNED_FRAME_PTRS.add(self._pinned.data_ptr())
         else:
             self._array = np.ascontiguousarray(a)
         self._key = key
         self._dataset_key = dataset_key
+
+    def __del__(self):
+        p = getattr(self, "_pinned", None)
+        if p is not None:
+            PINNED_FRAME_PTRS.discard(p.data_ptr())
 
     @property
     def path_original(self) -> str:

@@ -110,8 +110,12 @@ def run_sharded(app, images: Sequence, merge: bool = True, as_rows: bool = False
     mine = shard_indices(len(images), rank, ws)
     rows, failure = np.zeros((0, 6), np.float64), None
     try:
-        local = app.run_inference_on_images([images[j] for j in mine], merge=merge) if mine else []
-        rows = _rows_of(local, mine)
+        if mine and merge and hasattr(app, "run_inference_rows"):
+            rows = app.run_inference_rows([images[j] for j in mine])        # arrays end to end, no box objects
+            rows[:, 0] = np.asarray(mine, np.float64)[rows[:, 0].astype(np.int64)]
+        else:
+            local = app.run_inference_on_images([images[j] for j in mine], merge=merge) if mine else []
+            rows = _rows_of(local, mine)
     except Exception as e:           # noqa: BLE001 -- the flag must reach the collective whatever happened
         failure = e
     try:

@@ -179,6 +179,20 @@ class CascadeEngine:
         self._keepalive2 = (buf, slots, dense, win_off, win_pitch)
         return native.make_source(gather_base=buf, win_off=win_off, win_pitch=win_pitch)
 
+    @staticmethod
+    def _all_pinned(frames: Sequence[np.ndarray]) -> bool:
+        """True when every frame is a contiguous array in page-locked memory (registry of ``ArrayImageInfo(pin=True)``
+        first, the driver's answer otherwise)."""
+        from .data.image_info import PINNED_FRAME_PTRS
+        for f in frames:
+            if not f.flags["C_CONTIGUOUS"]:
+                return False
+            if f.__array_interface__["data"][0] in PINNED_FRAME_PTRS:
+                continue
+            if not f.flags["WRITEABLE"] or not torch.from_numpy(f).is_pinned():
+                return False
+        return True
+
     def _pinned_stage(self, nbytes: int) -> torch.Tensor:
         """The pinned staging buffer (grown on demand).  Before it is handed out again the H2D copies issued from
         it by the previous user must have finished: they are asynchronous and the host is about to overwrite it."""
@@ -366,12 +380,11 @@ class CascadeEngine:
         need = n * h * w * 3
         # frames that already live in page-locked memory (``ArrayImageInfo(..., pin=True)``, capture buffers) are
         # copied straight from where they are: n asynchronous H2D copies, no host-side gather
-        tens = [torch.from_numpy(f) if f.flags["C_CONTIGUOUS"] and f.flags["WRITEABLE"] else None for f in frames]
-        if all(t is not None and t.is_pinned() for t in tens):
+        tens = frames
+        if self._all_pinned(frames):
             with torch.cuda.device(self.device):
                 dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
-                for i, t in enumerate(tens):
-                    dev[i].copy_(t, non_blocking=True)
+                native.upload_frames(frames, dev, [i * h * w * 3 for i in range(n)])
             self._keepalive_host = tens
             return dev
         buf = self._pinned_stage(need)
@@ -595,14 +608,11 @@ class CascadeEngine:
             total = int(sum(sizes))
             shapes = [(frames[i].shape[0], frames[i].shape[1]) for i in order]
             # frames that already live in page-locked memory go straight to their slot of the flat device buffer
-            tens = [torch.from_numpy(frames[i]) if frames[i].flags["C_CONTIGUOUS"] and frames[i].flags["WRITEABLE"] else None
-                    for i in order]
-            if all(t is not None and t.is_pinned() for t in tens):
+            tens = [frames[i] for i in order]
+            if self._all_pinned(tens):
                 flat = torch.empty((total,), dtype=torch.uint8, device=self.device)
-                offs, o = [], 0
-                for t, sz in zip(tens, sizes):
-                    flat[o:o + sz].copy_(t.reshape(-1), non_blocking=True)
-                    offs.append(o); o += sz
+                offs = np.concatenate([[0], np.cumsum(sizes[:-1])]).astype(np.int64).tolist() if sizes else []
+                native.upload_frames([frames[i] for i in order], flat, offs)
                 self._keepalive_host = tens
                 return MixedFrames(flat=flat, offs=offs, shapes=shapes, groups={k: len(v) for k, v in groups.items()}, order=order)
             # otherwise: one pinned staging buffer with all frames (group order) -> one H2D copy

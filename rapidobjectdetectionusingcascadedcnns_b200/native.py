@@ -198,6 +198,17 @@ def window_scaled_rows(meta: torch.Tensor, slot: torch.Tensor, n: int, slots: to
     return win_off, win_pitch, err
 
 
+def upload_frames(frames: Sequence[np.ndarray], flat: torch.Tensor, offs: Sequence[int]) -> None:
+    """Asynchronous H2D copies of page-locked host frames into ``flat`` at byte offsets ``offs`` (one library call)."""
+    _require_cuda(flat)
+    n = len(frames)
+    ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+    sizes = np.asarray([f.nbytes for f in frames], np.int64)
+    o = np.asarray(offs, np.int64)
+    check(_lib.lib().rodc_upload_frames(ptrs, sizes.ctypes.data_as(_lib.c_i64p), o.ctypes.data_as(_lib.c_i64p), n,
+                                        _ptr(flat), _stream()), "rodc_upload_frames")
+
+
 class FrameTable:
     """Device table of the original frames for the RECROP source: one flat u8 buffer plus
     per-frame byte offsets and (H, W)."""

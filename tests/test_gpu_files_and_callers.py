@@ -262,3 +262,21 @@ def test_decode_upload_pipeline_from_files(pkg, tmp_path):
     pkg.cf.set("max_windows_per_launch", 1 << 18)
     with pytest.raises(ValueError):
         app.run_inference_on_images([pkg.FileImageInfo(bad), pkg.FileImageInfo(missing)], merge=True)
+
+
+@pytest.mark.parametrize("enlarge", [False, True])
+def test_row_output_equals_box_lists(pkg, enlarge):
+    """``run_inference_rows`` (what ``dist.run_sharded`` exchanges) == the flattened per-image box lists, for frames of
+    several shapes, with and without the vertical enlargement (`data/rectangles.py:185-220`)."""
+    g, frames, weights, _ = case_inputs("cascade_small_reject")
+    _set_cf(pkg, g["meta"]["cf"])
+    pkg.cf.set("vertically_enlarge_bboxes", enlarge)
+    app = pkg.InferenceCascadeApp("rows", stage_models=[pkg.StageModel(w) for w in weights])
+    infos = [pkg.ArrayImageInfo(f, "r_%d.png" % i, pin=(i % 2 == 0)) for i, f in enumerate(frames)]
+    infos.insert(1, pkg.ArrayImageInfo(np.zeros((8, 8, 3), np.uint8), "tiny.png"))      # yields no window: skipped
+    lists = app.run_inference_on_images(infos, merge=True)
+    rows = app.run_inference_rows(infos)
+    np.testing.assert_array_equal(rows, _rows(lists))
+    assert lists[1] == [] and not (rows[:, 0] == 1).any()
+    if enlarge:
+        assert rows.shape[0] and (rows[:, 2] != np.floor(rows[:, 2])).any()              # float ymin after the enlargement
