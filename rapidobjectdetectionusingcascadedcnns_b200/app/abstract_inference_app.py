@@ -170,16 +170,22 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
             log.log(" -> extract")
             # 1. plan: image sizes from the file HEADERS (no decode), window counts from the planner
             usable = []                                       # (input index, image, stage-0 windows)
+            per_shape = {}                                    # (h, w) -> window count or the ValueError of that shape
             for idx, img in enumerate(images):
                 hw = self._frame_size(img)
                 if hw is None:
                     continue
-                try:
-                    n_win = self._windows_per_frame(hw[1], hw[0])      # raises if a window leaves its level
-                    if n_win < 1:
-                        raise ValueError("Could not extract any windows from the given image")
-                except ValueError as e:
-                    log.log(" .. Skipped {}: {}".format(getattr(img, "path_resized", img), e))   # `:165-183`
+                n_win = per_shape.get(hw)
+                if n_win is None:
+                    try:
+                        n_win = self._windows_per_frame(hw[1], hw[0])      # raises if a window leaves its level
+                        if n_win < 1:
+                            raise ValueError("Could not extract any windows from the given image")
+                    except ValueError as e:
+                        n_win = e
+                    per_shape[hw] = n_win
+                if isinstance(n_win, ValueError):
+                    log.log(" .. Skipped {}: {}".format(getattr(img, "path_resized", img), n_win))   # `:165-183`
                     continue
                 usable.append((idx, img, n_win))
             timer_extracting.stop()

@@ -202,7 +202,7 @@ def upload_frames(frames: Sequence[np.ndarray], flat: torch.Tensor, offs: Sequen
     """Asynchronous H2D copies of page-locked host frames into ``flat`` at byte offsets ``offs`` (one library call)."""
     _require_cuda(flat)
     n = len(frames)
-    ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+    ptrs = (C.c_void_p * n)(*[f.__array_interface__["data"][0] for f in frames])
     sizes = np.asarray([f.nbytes for f in frames], np.int64)
     o = np.asarray(offs, np.int64)
     check(_lib.lib().rodc_upload_frames(ptrs, sizes.ctypes.data_as(_lib.c_i64p), o.ctypes.data_as(_lib.c_i64p), n,
