@@ -141,6 +141,13 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int n_tile = blockIdx.x % T::N_TILES, m_tile = blockIdx.x / T::N_TILES;
     const int m0 = m_tile * BM, n0 = n_tile * BN_;
     const int num_chunks = (num_kb + kc - 1) / kc;
+#ifdef RODC_PROBES
+    const int a_wrap = probe_hi_only >> 8;              // probe: every M tile reads the SAME a_wrap rows of A (L2 resident)
+    probe_hi_only &= 1;
+    const int m0a = a_wrap ? m0 % a_wrap : m0;
+#else
+    const int m0a = m0;
+#endif
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
@@ -171,14 +178,14 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 #ifdef RODC_PROBES
                 if (probe_hi_only) {            // bandwidth probe (wrong numerics): half the bytes, same MMAs
                     mbar_expect_tx(full, A_TILE + B_TILE);
-                    tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
+                    tma_load_2d(base, &map_a_hi, full, kb * BK, m0a);
                     tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
                     continue;
                 }
 #endif
                 mbar_expect_tx(full, STAGE_BYTES);
-                tma_load_2d(base, &map_a_hi, full, kb * BK, m0);
-                tma_load_2d(base + A_TILE, &map_a_lo, full, kb * BK, m0);
+                tma_load_2d(base, &map_a_hi, full, kb * BK, m0a);
+                tma_load_2d(base + A_TILE, &map_a_lo, full, kb * BK, m0a);
                 tma_load_2d(base + 2 * A_TILE, &map_b_hi, full, kb * BK, n0);
                 tma_load_2d(base + 2 * A_TILE + B_TILE, &map_b_lo, full, kb * BK, n0);
             }
@@ -336,6 +343,13 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int m0 = m_pair * (2 * BM) + (int)rank * BM;      // this CTA's 128 rows
     const int n0 = n_tile * BN_;
     const int num_chunks = (num_kb + kc - 1) / kc;
+#ifdef RODC_PROBES
+    const int a_wrap = probe_hi_only >> 8;              // probe: every M tile reads the SAME a_wrap rows of A (L2 resident)
+    probe_hi_only &= 1;
+    const int m0a = a_wrap ? m0 % a_wrap : m0;
+#else
+    const int m0a = m0;
+#endif
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(smem_u32(&bar_full[s]), 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
@@ -367,15 +381,15 @@ fc1_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (probe_hi_only) {            // bandwidth probe (wrong numerics)
                     if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * (A_TILE + B_HALF_TILE));
                     else mbar_arrive_cluster(full_leader);
-                    tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
+                    tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0a);
                     tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
                     continue;
                 }
 #endif
                 if (leader) mbar_expect_tx(smem_u32(&bar_full[s]), 2 * STAGE2_BYTES);   // both CTAs' bytes land here
                 else mbar_arrive_cluster(full_leader);
-                tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0);
-                tma_load_2d_2sm(base + A_TILE, &map_a_lo, full_leader, kb * BK, m0);
+                tma_load_2d_2sm(base, &map_a_hi, full_leader, kb * BK, m0a);
+                tma_load_2d_2sm(base + A_TILE, &map_a_lo, full_leader, kb * BK, m0a);
                 tma_load_2d_2sm(base + 2 * A_TILE, &map_b_hi, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
                 tma_load_2d_2sm(base + 2 * A_TILE + B_HALF_TILE, &map_b_lo, full_leader, kb * BK, n0 + (int)rank * BN_HALF);
             }
@@ -571,7 +585,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
             (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, 128)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, 128))) return rc;
         RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
         fc1_tc_kernel<128, 3><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                                  (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
+                                                                                  (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only() | (probe_a_wrap(s->in_size) << 8), m_dev, m_off);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
@@ -582,7 +596,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
         RODC_CUDA(cudaFuncSetAttribute(fc1_tc2_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
         const unsigned pairs = (unsigned)((m + 2 * BM - 1) / (2 * BM)) * P::N_TILES;      // (M pairs) x (N tiles)
         fc1_tc2_kernel<256, 3><<<pairs * 2u, THREADS, P::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                           (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
+                                                                           (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only() | (probe_a_wrap(s->in_size) << 8), m_dev, m_off);
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }
@@ -591,7 +605,7 @@ int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_l
         (rc = make_map(&mb_hi, s->fc1_hi, s->fc1_size, s->K, BN)) || (rc = make_map(&mb_lo, s->fc1_lo, s->fc1_size, s->K, BN))) return rc;
     RODC_CUDA(cudaFuncSetAttribute(fc1_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     fc1_tc_kernel<256, 2><<<m_tiles * T::N_TILES, THREADS, T::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s->fc1_b, bott, ld_bott, (int)m,
-                                                                              (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only(), m_dev, m_off);
+                                                                              (int)(s->K / BK), fc1_chunk_kblocks(), out_scale, fc1_probe_hi_only() | (probe_a_wrap(s->in_size) << 8), m_dev, m_off);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
 }

@@ -216,16 +216,19 @@ __global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev sr
             else { const int d = t - S; cv_tap(d, c.sh, S, false, sidx, a0, a1); tabs[3 * S + d] = sidx; tabs[4 * S + d] = a0; tabs[5 * S + d] = a1; }
         }
         __syncthreads();
-        int xo[4], xlen[4], xa0[4], xa1[4];                     // byte offset of the first x tap, bytes to fetch, weights
+        int xo[4], xlen[4];                                     // byte offset of the first x tap, bytes to fetch
+        uint32_t xw[4];                                         // the two x weights of a pixel as 16-bit halves (<= 2048 each)
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int x = 4 * u + i, sx = tabs[x];
             xo[i] = sx * 3;
             xlen[i] = sx + 1 <= c.sw - 1 ? 6 : 3;               // right border: the second tap is the same pixel (weight 0)
-            xa0[i] = tabs[S + x]; xa1[i] = tabs[2 * S + x];
+            xw[i] = (uint32_t)tabs[S + x] | ((uint32_t)tabs[2 * S + x] << 16);
         }
         for (int r = r0; r < S; r += RPP) {
-            const int sy = tabs[3 * S + r], b0 = tabs[4 * S + r], b1 = tabs[5 * S + r];
+            const int sy = tabs[3 * S + r];
+            // (b * t) >> 16 == umulhi(b << 16, t) for b <= 2048, t < 2^16: one IMAD.HI instead of a multiply and a shift
+            const uint32_t b0s = (uint32_t)tabs[4 * S + r] << 16, b1s = (uint32_t)tabs[5 * S + r] << 16;
             const int y0 = min(max(sy, 0), c.sh - 1), y1 = min(max(sy + 1, 0), c.sh - 1);
             const uint8_t* p0 = c.base + (int64_t)y0 * c.pitch;
             const uint8_t* p1 = c.base + (int64_t)y1 * c.pitch;
@@ -235,16 +238,16 @@ __global__ void __launch_bounds__((S / 4) * RPP) recrop_windows_kernel(SrcDev sr
                 uint32_t l0, h0, l1, h1;                        // the two taps of both rows: 6 adjacent bytes each
                 load_taps(p0 + xo[i], xlen[i], l0, h0);
                 load_taps(p1 + xo[i], xlen[i], l1, h1);
-                // xlen == 3: the bytes of the "second tap" are undefined, but its weight xa1 is 0 (cv_tap clamps f to 0)
+                // xlen == 3: the bytes of the "second tap" are undefined, but its weight is 0 (cv_tap clamps f to 0)
                 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const int t00 = (int)((l0 >> (8 * ch)) & 255u), t10 = (int)((l1 >> (8 * ch)) & 255u);
-                    const int t01 = ch == 0 ? (int)(l0 >> 24) : (int)((h0 >> (8 * (ch - 1))) & 255u);
-                    const int t11 = ch == 0 ? (int)(l1 >> 24) : (int)((h1 >> (8 * (ch - 1))) & 255u);
-                    const int T0 = t00 * xa0[i] + t01 * xa1[i];
-                    const int T1 = t10 * xa0[i] + t11 * xa1[i];
+                    // bytes (ch, 3 + ch) of the six = this channel of the two taps -> the low half of a register, then the
+                    // horizontal interpolation t0 * a0 + t1 * a1 is ONE dp2a (16-bit weights x 8-bit pixels, exact)
+                    const uint32_t sel = ch == 0 ? 0x4430u : (ch == 1 ? 0x4441u : 0x4452u);
+                    const uint32_t T0 = __dp2a_lo(xw[i], __byte_perm(l0, h0, sel), 0u);
+                    const uint32_t T1 = __dp2a_lo(xw[i], __byte_perm(l1, h1, sel), 0u);
                     // weights are >= 0 and sum to 2048 per axis, so the result is already inside 0..255
-                    const uint32_t v = (uint32_t)((((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2) & 255u;
+                    const uint32_t v = ((__umulhi(b0s, T0 >> 4) + __umulhi(b1s, T1 >> 4) + 2u) >> 2) & 255u;
                     const int b = i * 3 + ch;
                     w[b >> 2] |= v << (8 * (b & 3));
                 }
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, StreamCfg<S>::CTAS_PER_SM)
 features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                       const int64_t* __restrict__ n_dev, int64_t n_off) {
+                       const int64_t* __restrict__ n_dev, int64_t n_off, int probe_wrap) {
     n = eff_count(n, n_dev, n_off);
     constexpr int NQ = StreamCfg<S>::NQ, WPW = StreamCfg<S>::WPW, WPC = StreamCfg<S>::WPC, RQ = S / NQ;
     constexpr int VW = S * WPW;                                           // pixels of a warp row
@@ -589,9 +592,14 @@ features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t
         // all lane groups) covers G x 32 contiguous bytes
         constexpr int G = S / NP;                              // lane groups per window
         constexpr int PIX = OUT_SPLIT ? G * 16 : C;            // element stride between a thread's pixels
+#ifdef RODC_PROBES
+        const int64_t wout = probe_wrap ? wrel % probe_wrap : wrel;     // probe: A stays inside probe_wrap rows (L2 resident)
+#else
+        const int64_t wout = wrel;
+#endif
         int64_t oofs = OUT_SPLIT
-            ? wrel * (int64_t)S * S * C + (int64_t)(ya - 2) * S * C + cg * S * 16 + (xbase / NP) * 16 + 4 * t
-            : wrel * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
+            ? wout * (int64_t)S * S * C + (int64_t)(ya - 2) * S * C + cg * S * 16 + (xbase / NP) * 16 + 4 * t
+            : wout * (int64_t)S * S * C + (int64_t)xbase * C + 16 * cg + 4 * t + (int64_t)(ya - 2) * S * C;
         asm volatile("" : "+l"(oofs));
         const int64_t lo_delta = OUT_SPLIT ? out_lo - out_hi : 0;
         const uint32_t* abase = reinterpret_cast<const uint32_t*>(inh + xbase * 4) + t;
@@ -944,7 +952,8 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
             const unsigned g3 = (unsigned)(n < 148 * StreamCfg<ST_>::CTAS_PER_SM ? n : 148 * StreamCfg<ST_>::CTAS_PER_SM);  \
             features_stream_kernel<SPLIT, ST_><<<g3, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,       \
                                                                                  ldexpf(1.f, s->a_exp - s->c_exp),          \
-                                                                                 ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo, n_dev, n_off); \
+                                                                                 ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo, n_dev, n_off, \
+                                                                                 SPLIT ? probe_a_wrap(ST_) : 0); \
         } while (0)
         if (out_f32) { if (S == 12) RODC_LAUNCH_FEAT3(0, 12); else if (S == 24) RODC_LAUNCH_FEAT3(0, 24); else RODC_LAUNCH_FEAT3(0, 48); }
         else { if (S == 12) RODC_LAUNCH_FEAT3(1, 12); else if (S == 24) RODC_LAUNCH_FEAT3(1, 24); else RODC_LAUNCH_FEAT3(1, 48); }

@@ -4,6 +4,7 @@
 #include "stage.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -51,6 +52,22 @@ int prepare_fc1_split(rodc_stage* s, cudaStream_t st) {
                                                  s->kperm_side);
     RODC_LAUNCH_CHECK();
     return RODC_OK;
+}
+
+int probe_a_wrap(int in_size) {
+#ifdef RODC_PROBES
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RODC_PROBE_A_WRAP");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || (v % 256) != 0) v = 0;
+        if (v) fprintf(stderr, "librodc: RODC_PROBE_A_WRAP=%d is active -- the 48-px stage produces WRONG results (probe build)\n", v);
+    }
+    return in_size == 48 ? v : 0;
+#else
+    (void)in_size;
+    return 0;
+#endif
 }
 
 static int upload(float** dst, const float* src, size_t n) {

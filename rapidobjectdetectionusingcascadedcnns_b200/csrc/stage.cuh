@@ -83,5 +83,9 @@ int launch_fc2_softmax(const rodc_stage* s, const float* bott, int ld_bott, int6
 int launch_fc1_tensor(const rodc_stage* s, const __half* a_hi, const __half* a_lo, int64_t m,
                       float* bott, int ld_bott, cudaStream_t st, const int64_t* m_dev = nullptr, int64_t m_off = 0);
 int prepare_fc1_split(rodc_stage* s, cudaStream_t st);
+// -DRODC_PROBES builds only (0 otherwise): RODC_PROBE_A_WRAP=<rows> makes the 48-px stage keep its whole A operand in
+// `rows` rows (the feature kernel writes window w to row w mod rows, fc1 reads those rows for every M tile): the A planes
+// stay L2 resident, results are WRONG -- the measured upper bound of what producer fusion / L2 blocking could return
+int probe_a_wrap(int in_size);
 
 }  // namespace rodc

@@ -83,3 +83,14 @@ def test_planner_rejects_bad_arguments(L):
     from rapidobjectdetectionusingcascadedcnns_b200 import native
     assert native.Plan(10, 10, 12).n_windows == 0            # frame smaller than the window
     assert L.rodc_compact_scratch_bytes(5061) > 0 and L.rodc_group_scratch_bytes(100, 3) > 0
+
+
+def test_shipped_library_contains_no_probe_switches():
+    """Measurement aids that change numerics (RODC_FC1_PROBE_HI_ONLY, RODC_FC1_KC, RODC_PROBE_A_WRAP) exist only in a
+    -DRODC_PROBES build; the shipped librodc.so must not even contain their names."""
+    from rapidobjectdetectionusingcascadedcnns_b200 import build
+    blob = open(build.build_library(), "rb").read()
+    for name in (b"RODC_FC1_PROBE_HI_ONLY", b"RODC_FC1_KC", b"RODC_PROBE_A_WRAP"):
+        assert name not in blob, name
+    for name in (b"RODC_FC1_2CTA", b"RODC_FC1_BN", b"RODC_FEATURES_GENERIC"):        # bit-identical kernel choices stay
+        assert name in blob, name
