@@ -2,8 +2,8 @@
 // (data/image_info.py:201-250 via scipy.misc.imresize): horizontal pass -> u8 -> vertical pass
 // -> u8, 22-bit fixed-point coefficients precomputed on the host (plan.cu).
 //
-// Data movement: the horizontal kernel stages four source rows in shared memory ONCE (planar per
-// channel) and emits those rows of every level (so the frame is read once per batch, not once per
+// Data movement: the horizontal kernel brings four source rows into shared memory ONCE with a TMA bulk copy,
+// re-lays them planar per channel and emits those rows of every level (so the frame is read once per batch, not once per
 // scale, and the coefficient table once per four rows) with packed dp4a arithmetic; the vertical
 // kernel streams the horizontal rows with coalesced row-wise accesses.
 #include "common.cuh"
@@ -30,15 +30,42 @@ __global__ void __launch_bounds__(256) pyr_hpass_kernel(const uint8_t* __restric
                                                         const uint4* __restrict__ coef,
                                                         uint8_t* __restrict__ scratch, int64_t scratch_bytes) {
     extern __shared__ __align__(16) uint8_t rowsm[];
+    __shared__ __align__(8) uint64_t bar;
     const int y0 = blockIdx.x * HROWS, f = blockIdx.y;
     const int wpad = ((W + 3) & ~3) + 4;                    // words past W only ever meet zero coefficients
+    // 1. The HROWS source rows are ONE contiguous run of the frame: a single TMA bulk copy (cp.async.bulk, UBLKCP)
+    //    brings them into shared memory -- each source pixel is fetched from HBM once per batch, by the copy engine,
+    //    not by per-thread byte loads.  The run is widened to 16-byte boundaries (the copy's granularity): only
+    //    16-byte words that hold a byte of the rows are read, so nothing outside the frames buffer is touched.
+    uint8_t* raw = rowsm + (size_t)HROWS * 3 * wpad;        // [<= HROWS * W * 3 + 30], 16-byte aligned (wpad % 4 == 0, HROWS = 4)
+    const int nrows = min(HROWS, H - y0);
+    const uint8_t* src = frames + ((int64_t)f * H + y0) * W * 3;
+    const int lead = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint32_t nbytes = (uint32_t)((lead + nrows * W * 3 + 15) & ~15);
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(raw)), "l"(reinterpret_cast<uint64_t>(src - lead)), "r"(nbytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads();                                        // barrier initialised before anybody polls it
+    {
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_a) : "memory");
+        } while (!done);
+    }
+    // 2. interleaved RGB -> planar channel rows (the dp4a taps want four pixels of ONE channel per word)
     for (int r = 0; r < HROWS; ++r) {
         uint8_t* rs = rowsm + (size_t)r * 3 * wpad;
-        const int y = min(y0 + r, H - 1);                   // rows past H are computed from row H-1 and not stored
-        const uint8_t* src = frames + ((int64_t)f * H + y) * W * 3;
+        const uint8_t* q0 = raw + lead + (size_t)min(r, nrows - 1) * W * 3;   // rows past H repeat row H-1 and are not stored
         for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            const uint8_t* q = src + x * 3;
-            rs[x] = __ldg(q); rs[wpad + x] = __ldg(q + 1); rs[2 * wpad + x] = __ldg(q + 2);
+            const uint8_t* q = q0 + x * 3;
+            rs[x] = q[0]; rs[wpad + x] = q[1]; rs[2 * wpad + x] = q[2];
         }
         for (int x = W + threadIdx.x; x < wpad; x += blockDim.x) { rs[x] = 0; rs[wpad + x] = 0; rs[2 * wpad + x] = 0; }
     }
@@ -202,7 +229,8 @@ extern "C" int rodc_pyramid(rodc_plan* p, const uint8_t* frames, int n_frames, u
     const int nl = (int)p->levels.size();
     bool any_resample = false;
     for (auto& l : p->levels) any_resample |= !l.identity;
-    const size_t smem = (size_t)HROWS * 3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4);
+    // planar rows + the raw rows of the bulk copy (widened to 16-byte boundaries on both sides)
+    const size_t smem = (size_t)HROWS * 3 * ((((size_t)p->img_w + 3) & ~(size_t)3) + 4) + (size_t)HROWS * p->img_w * 3 + 32;
     if (any_resample && smem > 48 * 1024)
         RODC_CUDA(cudaFuncSetAttribute(pyr_hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t frame_bytes = (int64_t)p->img_h * p->img_w * 3;

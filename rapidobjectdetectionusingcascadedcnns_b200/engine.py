@@ -542,7 +542,8 @@ class CascadeEngine:
             self._enqueue_nosync(g["frames"], plan, g["ws"], g["table"])   # eager warm-up: plan upload, kernel attributes
             torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: the app's feeder thread may allocate / copy on its own stream while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self._enqueue_nosync(g["frames"], plan, g["ws"], g["table"])
                 g["h_counts"].copy_(out["counts"], non_blocking=True)
                 if "rows" in out:
