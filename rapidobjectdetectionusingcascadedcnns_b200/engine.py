@@ -659,11 +659,15 @@ class CascadeEngine:
             slot_groups: List[dict] = []
             fbase = wbase = pbase = sbase = 0
             pos = 0
+            # ONE horizontal-pass scratch for all shape groups (their K1 launches run one after the other on this stream)
+            scratch_all = torch.empty((max(n * plans[k].scratch_bytes for k, n in mf.groups.items()),), dtype=torch.uint8,
+                                      device=self.device)
             for k, n in mf.groups.items():
                 p = plans[k]
                 fsz = k[0] * k[1] * 3
                 d = flat[offs[pos]:offs[pos] + n * fsz].view(n, k[0], k[1], 3)
-                native.pyramid(p, d, out=pyr[pbase:pbase + n * p.pyramid_bytes].view(n, p.pyramid_bytes))
+                native.pyramid(p, d, out=pyr[pbase:pbase + n * p.pyramid_bytes].view(n, p.pyramid_bytes),
+                               scratch=scratch_all[:n * p.scratch_bytes].view(n, p.scratch_bytes))
                 nw = n * p.n_windows
                 native.window_gather_rows(p, n, pbase, win_off[wbase:wbase + nw], win_pitch[wbase:wbase + nw])
                 native.window_meta(p, n, fbase, self.device, out=meta0[wbase:wbase + nw])
