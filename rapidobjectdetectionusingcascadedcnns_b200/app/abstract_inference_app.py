@@ -94,31 +94,12 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
         payload = self._upload_frame_batch([frames[k] for k in keep])
         return [chunk[k][0] for k in keep], [imgs[k] for k in keep], payload, None
 
-    def _chunk_feeder(self, chunks, in_memory: bool = False):
-        """Generator over prepared chunks, always one upload ahead of the consumer.
-
-        In-memory images need no CPU work, so no thread either: the (asynchronous) upload of chunk k + 1 is issued
-        on a side stream right before chunk k is handed out, and the copy engine works while the caller sits in
-        chunk k's count reads.  Files are decoded by a feeder thread with a pool of ``cf decode_threads`` workers,
-        which uploads from two alternating pinned staging buffers up to two chunks ahead.  (A feeder thread for
-        in-memory frames was measured: its Python loops and the launch loop of the caller take turns on the GIL at
-        the interpreter's 5 ms switch interval and the GPU starves -- 0.78 instead of 0.95 of the resident rate.)"""
+    def _chunk_feeder(self, chunks):
+        """Generator over prepared chunks of FILES: a feeder thread decodes them with a pool of ``cf decode_threads``
+        workers and uploads from two alternating pinned staging buffers on its own stream, up to two chunks ahead of
+        the consumer.  (In-memory frames do not come here, see ``_run_chunks_in_memory``.)"""
         import torch
         device = self._engine.device
-        if in_memory:
-            side = torch.cuda.Stream(device=device)
-
-            def prepare(k):
-                with torch.cuda.stream(side):
-                    ids, infos, payload, _ = self._prepare_chunk(chunks[k], None, 1 + (k & 1))
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                return ids, infos, payload, ev
-            nxt = prepare(0) if chunks else None
-            for k in range(len(chunks)):
-                cur, nxt = nxt, (prepare(k + 1) if k + 1 < len(chunks) else None)
-                yield cur
-            return
         import queue
         import sys
         import threading
@@ -164,6 +145,40 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
                 except queue.Empty:
                     t.join(timeout=0.05)
             sys.setswitchinterval(old_interval)
+
+    def _run_chunks_in_memory(self, chunks, as_rows: bool):
+        """Several chunks of frames that need no decoding: no thread.  While the GPU works on stage 0 of chunk k (tens of
+        milliseconds for a full chunk) the host prepares chunk k + 1 and issues its asynchronous upload on a side stream
+        -- the engine calls back right after stage 0 has been enqueued, before the first count read.  (A feeder THREAD
+        for in-memory frames was measured: its Python loops and the caller's launch loop take turns on the GIL at the
+        interpreter's 5 ms switch interval and the GPU starves -- 0.78 instead of 0.95 of the resident rate.)"""
+        import torch
+        side = torch.cuda.Stream(device=self._engine.device)
+
+        def prepare(k):
+            with torch.cuda.stream(side):
+                ids, infos, payload, _ = self._prepare_chunk(chunks[k], None, 1 + (k & 1))
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return ids, infos, payload, ev
+        nxt = prepare(0)
+        for k in range(len(chunks)):
+            cur, nxt = nxt, None
+            state = {}
+
+            def ahead(k=k, state=state):
+                if k + 1 < len(chunks):
+                    state["next"] = prepare(k + 1)
+            ids, infos, payload, ev = cur
+            if ids:
+                self._wait_upload(ev, payload)
+                done = self._run_uploaded(infos, payload, as_rows=as_rows, while_busy=ahead)
+            else:
+                done = (np.zeros((0,), np.int64), np.zeros((0, 5), np.float64)) if as_rows else []
+            if "next" not in state:                         # the run took a path without the callback (latency graph)
+                ahead()
+            nxt = state.get("next")
+            yield ids, done
 
     @staticmethod
     def _wait_upload(event, payload):
@@ -231,13 +246,25 @@ class AbstractInferenceApp(metaclass=abc.ABCMeta):
             # thread, `data/image_info.py:228-240`).
             in_memory = all(getattr(i, "_array", None) is not None for _, i, _ in usable)
             n_done = 0
-            if len(chunks) == 1 and in_memory:
-                feed = [self._prepare_chunk(chunks[0], None, 0)]
+            if in_memory and len(chunks) > 1:
+                feed = self._run_chunks_in_memory(chunks, _as_rows)
+            elif in_memory:
+                feed = [self._prepare_chunk(chunks[0], None, 0)] if chunks else []
             else:
-                feed = self._chunk_feeder(chunks, in_memory)
+                feed = self._chunk_feeder(chunks)
             for item in feed:
                 if isinstance(item, BaseException):
                     raise item
+                if len(item) == 2:                             # (input indices, finished result) from the in-memory pipeline
+                    ids, done = item
+                    if _as_rows:
+                        local, rows = done
+                        row_parts.append(np.column_stack([np.asarray(ids, np.float64)[local], rows]).reshape(-1, 6))
+                    else:
+                        for idx, boxes in zip(ids, done):
+                            all_results[idx] = boxes
+                    n_done += len(ids)
+                    continue
                 ids, infos, payload, event = item
                 if not ids:
                     continue

@@ -160,20 +160,20 @@ class InferenceApp(AbstractInferenceApp):
     def _run_on_frame_batch(self, infos, frames) -> List[List[LabeledBoundingBox]]:
         return self._run_uploaded(infos, self._upload_frame_batch(frames))
 
-    def _run_uploaded(self, infos, payload, as_rows: bool = False):
+    def _run_uploaded(self, infos, payload, as_rows: bool = False, while_busy=None):
         """Run one uploaded chunk.  Returns one result list per frame, or with ``as_rows`` the arrays
         ``(frame index inside the chunk [K], rows [K,5] = xmin, ymin, xmax, ymax, confidence)`` without any object."""
         self._init_tf()
         self._update_input_dims()
         kind, data = payload
         if kind == "same":
-            res = self._engine.run_frames(data)
+            res = self._engine.run_frames(data, while_busy=while_busy)
             self._log_stage_stats(res)
             if as_rows:
                 return np.asarray(res.frame, np.int64), self._rows_from_result(res)
             return self._boxes_from_result(res, infos, len(infos))
         # several shapes: one merged set of stage launches (internal frame ids are grouped by shape)
-        res, order = self._engine.run_mixed_device(data), data.order
+        res, order = self._engine.run_mixed_device(data, while_busy=while_busy), data.order
         self._log_stage_stats(res)
         if as_rows:
             return np.asarray(order, np.int64)[np.asarray(res.frame, np.int64)], self._rows_from_result(res)

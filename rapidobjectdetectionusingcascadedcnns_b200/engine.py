@@ -243,7 +243,9 @@ class CascadeEngine:
 
     # ------------------------------------------------------------------ stages on a window set
     def _run_stages(self, src0, n0: int, meta0: torch.Tensor, table: native.FrameTable, n_frames: int,
-                    keep_trace: bool, origin: Optional[WindowOrigin] = None) -> GroupResult:
+                    keep_trace: bool, origin: Optional[WindowOrigin] = None, while_busy=None) -> GroupResult:
+        """``while_busy``: called ONCE, right after stage 0 has been enqueued and before its survivor count is read --
+        host work done there (preparing and uploading the next chunk) is hidden behind the GPU's stage-0 time."""
         dev = self.device
         impl = self._impl()
         n_st = len(self.stages)
@@ -289,6 +291,9 @@ class CascadeEngine:
                 bott_in=bott if use_b and nxt.n_prev > 0 else None, width=st.width,
                 bott_out=bott_next if use_b and nxt.n_prev > 0 else None, col_off=nxt.fc1_size if nxt is not None else 0,
                 conf_acc=conf_acc, conf_out=conf_out, conf_mode=conf_mode if conf_acc is not None else native.CONF_LAST)
+            if while_busy is not None:
+                hook, while_busy = while_busy, None
+                hook()
             kept = int(count.item())                                        # one host sync per stage
             res.stage_in.append(n); res.stage_kept.append(kept)
             if keep_trace:
@@ -560,7 +565,7 @@ class CascadeEngine:
                                         g["h_meta"].numpy() if "h_meta" in g else None,
                                         g["h_conf"].numpy() if "h_conf" in g else None, n0)
 
-    def run_frames(self, frames, keep_trace: bool = False) -> GroupResult:
+    def run_frames(self, frames, keep_trace: bool = False, while_busy=None) -> GroupResult:
         """Whole path for ``frames`` ``[n,H,W,3]`` uint8 (numpy: copied H2D; CUDA tensor: used in
         place).  Raises ValueError like the reference when no window can be extracted."""
         with torch.cuda.device(self.device):
@@ -595,7 +600,7 @@ class CascadeEngine:
             elif len(self.stages) > 1 and self._scaled_branch_possible():
                 origin = WindowOrigin(slot=native.window_levels(plan, n, 0, self.device),
                                       groups=[dict(frames=frames, frame_base=0, scales=plan.scale, width=plan.win)])
-            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, origin)
+            return self._run_stages(src0, n * plan.n_windows, meta0, table, n, keep_trace, origin, while_busy)
 
     def upload_mixed(self, frames: Sequence[np.ndarray]) -> "MixedFrames":
         """Host frames of DIFFERENT shapes -> one flat device buffer (frames grouped by shape, one asynchronous
@@ -635,7 +640,7 @@ class CascadeEngine:
         mf = self.upload_mixed(frames)
         return self.run_mixed_device(mf, keep_trace), mf.order
 
-    def run_mixed_device(self, mf: "MixedFrames", keep_trace: bool = False) -> GroupResult:
+    def run_mixed_device(self, mf: "MixedFrames", keep_trace: bool = False, while_busy=None) -> GroupResult:
         """``run_mixed`` for frames that are already resident (``upload_mixed``).  One K1 launch pair per shape
         writes into a shared pyramid buffer; stage 0 reads its windows through a per-window (offset, pitch)
         table, later stages re-crop from a table of all frames."""
@@ -679,7 +684,7 @@ class CascadeEngine:
             src0 = native.make_source(gather_base=pyr, win_off=win_off, win_pitch=win_pitch)
             self._keepalive0 = (pyr, win_off, win_pitch, flat, table)
             origin = WindowOrigin(gather=lambda: (pyr, win_off, win_pitch), slot=slot0, groups=slot_groups)
-            return self._run_stages(src0, n_windows, meta0, table, len(mf.order), keep_trace, origin)
+            return self._run_stages(src0, n_windows, meta0, table, len(mf.order), keep_trace, origin, while_busy)
 
     def run_windows(self, windows_raw, meta: np.ndarray, frames: List[np.ndarray], keep_trace: bool = False,
                     scales: Optional[np.ndarray] = None, widths: Optional[np.ndarray] = None) -> GroupResult:

@@ -280,3 +280,26 @@ def test_row_output_equals_box_lists(pkg, enlarge):
     assert lists[1] == [] and not (rows[:, 0] == 1).any()
     if enlarge:
         assert rows.shape[0] and (rows[:, 2] != np.floor(rows[:, 2])).any()              # float ymin after the enlargement
+
+
+def test_pinned_frames_are_uploaded_in_place(pkg):
+    """Frames in page-locked memory (``ArrayImageInfo(pin=True)``) take the one-call ``rodc_upload_frames`` path: the
+    device copy equals the frames (same shape and mixed shapes) and the results equal those of pageable frames."""
+    from rapidobjectdetectionusingcascadedcnns_b200.engine import CascadeEngine
+    g, frames, weights, _ = case_inputs("cascade_small_reject")
+    _set_cf(pkg, g["meta"]["cf"])
+    eng = CascadeEngine(weights)
+    pinned = [pkg.ArrayImageInfo(f, "p_%d" % i, pin=True).raw_original(True) for i, f in enumerate(frames)]
+    assert eng._all_pinned(pinned) and not eng._all_pinned(list(frames))
+    same = [pinned[0], pkg.ArrayImageInfo(frames[0][::-1].copy(), "p_r", pin=True).raw_original(True)]
+    dev = eng.upload_host_frames(same)
+    assert np.array_equal(dev.cpu().numpy(), np.stack(same))
+    mf = eng.upload_mixed(pinned)
+    for k, i in enumerate(mf.order):
+        h, w = mf.shapes[k]
+        assert np.array_equal(mf.flat[mf.offs[k]:mf.offs[k] + h * w * 3].cpu().numpy().reshape(h, w, 3), frames[i])
+    app = pkg.InferenceCascadeApp("pin", stage_models=[pkg.StageModel(w) for w in weights])
+    a = _rows(app.run_inference_on_images([pkg.ArrayImageInfo(f, "x_%d" % i, pin=True) for i, f in enumerate(frames)], merge=True))
+    b = _rows(app.run_inference_on_images([pkg.ArrayImageInfo(f, "x_%d" % i) for i, f in enumerate(frames)], merge=True))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, g["final_boxes"])

@@ -416,6 +416,49 @@ np.save(sys.argv[1], logits.cpu().numpy())
         assert np.array_equal(outs[0], o)            # same MMA order per element -> bit-identical
 
 
+@pytest.mark.parametrize("stage_idx", [0, 1, 2])
+def test_generic_feature_kernel_writes_the_same_k_order(nat, stage_idx):
+    """The split fc1 operand is stored in a permuted K order (stage.cuh kperm) that the prepared weights follow.  Both
+    producers must agree on it: the generic feature kernel (RODC_FEATURES_GENERIC=1, shared-memory pooling, bias added
+    after the MMA) gives the same logits as the streaming kernel up to the rounding of their different bias handling,
+    and both agree with the fp64 oracle."""
+    import os
+    import subprocess
+    import sys
+    from oracle import stage_net
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+from rapidobjectdetectionusingcascadedcnns_b200 import native
+from test_gpu_kernels import _stage_case
+S, w, x, bott_in = _stage_case(%d, n=97)
+st = native.Stage(w)
+bott = torch.zeros((97, st.width), dtype=torch.float32, device="cuda")
+if bott_in is not None:
+    bott[:, 512:] = torch.from_numpy(bott_in).cuda()
+ws = torch.empty((st.workspace_bytes(97),), dtype=torch.uint8, device="cuda")
+logits, _ = native.stage_forward(st, native.make_source(dense=torch.from_numpy(x).cuda()), 0, 97, bott, ws)
+np.save(sys.argv[1], logits.cpu().numpy())
+'''
+    from conftest import REPO
+    outs = []
+    for k, var in enumerate([dict(), dict(RODC_FEATURES_GENERIC="1")]):
+        path = os.path.join("/tmp", "rodc_feat_%d_%d.npy" % (stage_idx, k))
+        env = {kk: vv for kk, vv in os.environ.items() if not kk.startswith("RODC_FEATURES")}
+        env.update(var)
+        subprocess.run([sys.executable, "-c", code % (REPO, os.path.join(REPO, "tests"), stage_idx), path], check=True,
+                       env=env, timeout=300)
+        outs.append(np.load(path).astype(np.float64))
+    S, w, x, bott_in = _stage_case(stage_idx, n=97)
+    _, _, l64, _ = stage_net.stage_forward(x, w, bott_in, dtype=torch.float64)
+    l64 = l64.numpy()
+    scale = np.abs(l64).max()
+    for o in outs:
+        assert np.abs(o - l64).max() <= 2e-5 * scale
+    assert np.abs(outs[0] - outs[1]).max() <= 4e-6 * scale
+
+
 @pytest.mark.parametrize("spec", [
     dict(S=24, filters=(16, 32), ksize=3, conv_stride=1, pool_size=2, pool_stride=2, n_prev=512),
     dict(S=48, filters=(24,), ksize=5, conv_stride=2, pool_size=3, pool_stride=2, n_prev=0),
