@@ -485,8 +485,8 @@ template <int S> struct StreamCfg {
     static constexpr int INH = WPW == 2 ? INH0 + ((16 - (INH0 / 2) % 32 + 32) % 32) * 2 : INH0;
 };
 
-template <int OUT_SPLIT, int S>
-__global__ void __launch_bounds__(FEAT_THREADS, StreamCfg<S>::CTAS_PER_SM)
+template <int OUT_SPLIT, int S, int OCC = StreamCfg<S>::CTAS_PER_SM>
+__global__ void __launch_bounds__(FEAT_THREADS, OCC)
 features_stream_kernel(const uint8_t* __restrict__ dense, int64_t first, int64_t n,
                        const uint32_t* __restrict__ conv_frag, float pix_scale, float inv_a_scale,
                        float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
@@ -945,19 +945,30 @@ int launch_features(const rodc_stage* s, const SrcDev& src, int64_t first, int64
     // the streaming kernels read materialised u8 windows (rodc_stage_forward copies every other source into its
     // workspace first); other sources and sizes take the generic kernel
     if (!use_v2 && (S == 12 || S == 24 || S == 48) && src.kind == RODC_SRC_DENSE && (reinterpret_cast<uintptr_t>(src.dense) & 3) == 0) {
-#define RODC_LAUNCH_FEAT3(SPLIT, ST_)                                                                                      \
+#define RODC_LAUNCH_FEAT3_OCC(SPLIT, ST_, OCC_)                                                                            \
         do {                                                                                                              \
             const size_t smem = feat3_smem_bytes<ST_>();                                                                  \
-            RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            const unsigned g3 = (unsigned)(n < 148 * StreamCfg<ST_>::CTAS_PER_SM ? n : 148 * StreamCfg<ST_>::CTAS_PER_SM);  \
-            features_stream_kernel<SPLIT, ST_><<<g3, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm,       \
+            RODC_CUDA(cudaFuncSetAttribute(features_stream_kernel<SPLIT, ST_, OCC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            const unsigned g3 = (unsigned)(n < 148 * OCC_ ? n : 148 * OCC_);                                                \
+            features_stream_kernel<SPLIT, ST_, OCC_><<<g3, FEAT_THREADS, smem, st>>>(src.dense, first, n, s->conv_frag_perm, \
                                                                                  ldexpf(1.f, s->a_exp - s->c_exp),          \
                                                                                  ldexpf(1.f, -s->a_exp), out_f32, out_hi, out_lo, n_dev, n_off, \
                                                                                  SPLIT ? probe_a_wrap(ST_) : 0); \
         } while (0)
+#ifdef RODC_PROBES
+        // probe build: RODC_PROBE_FEAT_OCC3=1 runs the 24 / 48-px kernels with three CTAs per SM (80 registers, ~400 B
+        // of spills per thread) instead of two (128 registers, none): an occupancy experiment, same results
+        static int occ3 = -1;
+        if (occ3 < 0) { const char* e = getenv("RODC_PROBE_FEAT_OCC3"); occ3 = (e && e[0] == '1') ? 1 : 0; }
+#define RODC_LAUNCH_FEAT3(SPLIT, ST_)                                                                                      \
+        do { if (occ3 && ST_ != 12) RODC_LAUNCH_FEAT3_OCC(SPLIT, ST_, 3); else RODC_LAUNCH_FEAT3_OCC(SPLIT, ST_, StreamCfg<ST_>::CTAS_PER_SM); } while (0)
+#else
+#define RODC_LAUNCH_FEAT3(SPLIT, ST_) RODC_LAUNCH_FEAT3_OCC(SPLIT, ST_, StreamCfg<ST_>::CTAS_PER_SM)
+#endif
         if (out_f32) { if (S == 12) RODC_LAUNCH_FEAT3(0, 12); else if (S == 24) RODC_LAUNCH_FEAT3(0, 24); else RODC_LAUNCH_FEAT3(0, 48); }
         else { if (S == 12) RODC_LAUNCH_FEAT3(1, 12); else if (S == 24) RODC_LAUNCH_FEAT3(1, 24); else RODC_LAUNCH_FEAT3(1, 48); }
 #undef RODC_LAUNCH_FEAT3
+#undef RODC_LAUNCH_FEAT3_OCC
         RODC_LAUNCH_CHECK();
         return RODC_OK;
     }

@@ -90,7 +90,7 @@ def test_shipped_library_contains_no_probe_switches():
     -DRODC_PROBES build; the shipped librodc.so must not even contain their names."""
     from rapidobjectdetectionusingcascadedcnns_b200 import build
     blob = open(build.build_library(), "rb").read()
-    for name in (b"RODC_FC1_PROBE_HI_ONLY", b"RODC_FC1_KC", b"RODC_PROBE_A_WRAP"):
+    for name in (b"RODC_FC1_PROBE_HI_ONLY", b"RODC_FC1_KC", b"RODC_PROBE_A_WRAP", b"RODC_PROBE_FEAT_OCC3"):
         assert name not in blob, name
     for name in (b"RODC_FC1_2CTA", b"RODC_FC1_BN", b"RODC_FEATURES_GENERIC"):        # bit-identical kernel choices stay
         assert name in blob, name
