@@ -225,3 +225,39 @@ def test_fddb_caller_dense_pyramid(pkg, tmp_path):
     if ev.results[1][0]:
         b = ev.results[1][0][0]
         assert text[2] == "{} {} {} {} {}".format(b.xmin, b.ymin, b.width, b.height, b.confidence)
+
+
+def test_config3_mixed_batch_properties_at_scale(pkg):
+    """BASELINE config 3 shapes at a size the oracle cannot follow (140 frames of 35 shapes, ~850 k stage-0 windows,
+    several launch chunks): size-independent properties.  Results do not depend on the input order, on the chunking
+    or on the frame's neighbours in a batch; a second pass returns the same bytes; row output == box lists."""
+    from rapidobjectdetectionusingcascadedcnns_b200 import synth
+    weights = _weights([-40.0, -85.0, -24.0])
+    app = pkg.InferenceCascadeApp("c3", stage_models=[pkg.StageModel(w) for w in weights])
+    n = 140
+    frames = [synth.synth_frame(*synth.fddb_shape(j), 100 + j) for j in range(n)]
+    infos = [pkg.ArrayImageInfo(f, "c3_%d.png" % j, pin=(j % 3 == 0)) for j, f in enumerate(frames)]
+    a = [np.asarray(r.rows() if hasattr(r, "rows") else np.zeros((0, 5))) for r in app.run_inference_on_images(infos, merge=True)]
+    assert sum(x.shape[0] for x in a) > 50
+    # 1. idempotence
+    b = [np.asarray(r.rows() if hasattr(r, "rows") else np.zeros((0, 5))) for r in app.run_inference_on_images(infos, merge=True)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # 2. order independence (a permutation regroups the shape groups and the chunks)
+    perm = np.random.RandomState(0).permutation(n)
+    c = app.run_inference_on_images([infos[i] for i in perm], merge=True)
+    for k, i in enumerate(perm):
+        got = np.asarray(c[k].rows() if hasattr(c[k], "rows") else np.zeros((0, 5)))
+        assert np.array_equal(got, a[i]), i
+    # 3. chunking independence: many small launch sets (the in-memory pipeline with its stage-0 callback) vs one
+    pkg.cf.set("max_windows_per_launch", 60000)
+    d = [np.asarray(r.rows() if hasattr(r, "rows") else np.zeros((0, 5))) for r in app.run_inference_on_images(infos, merge=True)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, d))
+    rows = app.run_inference_rows(infos)
+    flat = np.concatenate([np.column_stack([np.full((x.shape[0],), float(i)), x]) for i, x in enumerate(a) if x.shape[0]])
+    assert np.array_equal(rows, flat)
+    # 4. merge=False (one image per call, the FDDB caller's mode) gives the same boxes
+    pkg.cf.set("max_windows_per_launch", 1 << 18)
+    for i in (0, 17, 139):
+        single = app.run_inference_on_images([infos[i]], merge=False)[0]
+        got = np.asarray(single.rows() if hasattr(single, "rows") else np.zeros((0, 5)))
+        assert np.array_equal(got, a[i])
