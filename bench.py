@@ -388,7 +388,15 @@ def main():
             last["file_rows"] = rdist.run_sharded(app, finfos, merge=True, as_rows=True)
         step_files()
         ms_files = timed(step_files, args.steps)
-        files = {"ms": ms_files, "disk_bytes": disk_bytes, "decode_threads": int(pkg.cf.get("decode_threads"))}
+        # the decode pool alone (no GPU work): the ceiling of the from-files rate on this host
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = int(pkg.cf.get("decode_threads"))
+        with ThreadPoolExecutor(max_workers=n_thr) as pool:
+            t0 = time.perf_counter()
+            list(pool.map(lambda p: pkg.FileImageInfo(p).raw_original(True), list(paths.values())))
+            decode_s = time.perf_counter() - t0
+        files = {"ms": ms_files, "disk_bytes": disk_bytes, "decode_threads": n_thr,
+                 "decode_only_fps": len(paths) / decode_s if decode_s > 0 else None}
         for p in paths.values():
             os.remove(p)
         os.rmdir(tmpdir)
@@ -498,6 +506,7 @@ def main():
             line["e2e_from_files"] = {"value": fps, "unit": UNIT, "format": "JPEG quality 95 written from the synthetic frames",
                                       "file_bytes_per_step_rank0": files["disk_bytes"], "decode_threads_per_rank": files["decode_threads"],
                                       "boxes_per_step": int(last["file_rows"].shape[0]), "ratio_to_resident": fps / value if value else None,
+                                      "decode_pool_alone_frames_per_s_rank0": files["decode_only_fps"],
                                       "api": "dist.run_sharded(app.run_inference_on_images([FileImageInfo...])): header-only planning, "
                                              "thread-pool decode and side-stream upload of chunk k + 1 overlap the compute of chunk k"}
         if ktable:

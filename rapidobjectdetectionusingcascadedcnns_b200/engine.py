@@ -583,8 +583,18 @@ class CascadeEngine:
                 raise ValueError("Could not extract any windows from the given image")      # abstract_inference_app.py:168-169
             if not plan.fits:
                 raise ValueError("xmax/ymax must not leave the image boundaries")           # rectangles.py:286-289
-            if not keep_trace and self._latency_eligible(n * plan.n_windows):
-                return self.run_frames_latency(frames)
+            if not keep_trace and not getattr(self, "_latency_broken", False) and self._latency_eligible(n * plan.n_windows):
+                try:
+                    return self.run_frames_latency(frames)
+                except (ValueError, native._lib.RodcError):
+                    raise
+                except RuntimeError as e:
+                    # stream capture can be refused by the environment (a tool that forbids it, a driver without graph
+                    # support for an op): the stage-by-stage path below runs the same kernels and returns the same bytes
+                    self._latency_broken = True
+                    self._graphs = {}
+                    from .utils import log
+                    log.log("CUDA-graph latency path disabled for this engine ({}); using the stage-by-stage path".format(e))
             pyr = native.pyramid(plan, frames)
             meta0 = native.window_meta(plan, n, 0, self.device)
             table = native.FrameTable.from_batch(frames)
