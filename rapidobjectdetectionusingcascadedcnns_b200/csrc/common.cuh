@@ -47,9 +47,9 @@ class Prof {
 public:
     Prof(int kc, cudaStream_t st, int sub = 0, double bytes = 0.0, double flops = 0.0, int launches = 1);
     ~Prof();
-    // device accumulator (one u64) for a data-dependent pixel count, NULL unless this scope is being recorded;
-    // 3 bytes per counted pixel are added to the scope's bytes at collect time
-    unsigned long long* area_slot();
+    // device accumulator (one u64) for a data-dependent count (K4: pixels of the crops, K3: survivors), NULL unless
+    // this scope is being recorded; bytes_per_unit x the accumulated count is added to the scope's bytes at collect time
+    unsigned long long* area_slot(double bytes_per_unit = 3.0);
     bool recording() const { return rec_ >= 0; }
 private:
     cudaStream_t st_;

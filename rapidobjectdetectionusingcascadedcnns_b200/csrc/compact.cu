@@ -120,6 +120,11 @@ __global__ void __launch_bounds__(256) compact_gather_rows_kernel(const int32_t*
     }
 }
 
+// measurement only (profile level 2): the survivor count of this compaction for the byte bookkeeping
+__global__ void compact_note_count_kernel(const int64_t* __restrict__ count, unsigned long long* __restrict__ slot) {
+    *slot = (unsigned long long)*count;
+}
+
 }  // namespace rodc
 
 using namespace rodc;
@@ -160,10 +165,9 @@ extern "C" int rodc_compact_dyn(const float* probs, int64_t n, const int64_t* n_
     }
     int32_t* tile = reinterpret_cast<int32_t*>(scratch);
     const int nt = (int)((n + CT - 1) / CT);
-    // 8 n (score reads of the two passes) + per survivor 24 B (meta + index) + 8 D_i (row gather, r + w).
-    // The survivor count is data dependent: bytes are booked for the worst case n survivors of the gather.
-    Prof prof(KC_COMPACT, st, width, 8.0 * (double)n + (double)n * 44.0 + (bott_in ? 8.0 * (double)n * width : 0.0), 0.0,
-              bott_in ? 4 : 3);
+    // 8 n (score reads of the two passes) + per SURVIVOR 44 B (meta r + w, index, confidence) + 8 D_i (row
+    // gather, r + w); the survivor count is data dependent and is noted on the device when the scope is recorded
+    Prof prof(KC_COMPACT, st, width, 8.0 * (double)n, 0.0, bott_in ? 4 : 3);
     compact_count_kernel<<<nt, CT, 0, st>>>(probs, n, n_dev, threshold, tile);
     RODC_LAUNCH_CHECK();
     compact_scan_kernel<<<1, 1024, 0, st>>>(tile, nt, count_out);
@@ -174,6 +178,10 @@ extern "C" int rodc_compact_dyn(const float* probs, int64_t n, const int64_t* n_
         int64_t blocks = (n + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
         compact_gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(keep_idx_out, count_out, bott_in, ld_in, width, bott_out, ld_out, col_off);
         RODC_LAUNCH_CHECK();
+    }
+    if (prof.recording()) {
+        if (unsigned long long* slot = prof.area_slot(44.0 + (bott_in ? 8.0 * width : 0.0)))
+            compact_note_count_kernel<<<1, 1, 0, st>>>(count_out, slot);
     }
     return RODC_OK;
 }

@@ -17,7 +17,7 @@ namespace rodc {
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<int> g_level{0};
 
-struct ProfRec { cudaEvent_t a, b; int kc, sub, launches; double bytes, flops; int area_slot; };
+struct ProfRec { cudaEvent_t a, b; int kc, sub, launches; double bytes, flops; int area_slot; double area_scale; };
 static std::mutex g_mu;
 static std::vector<ProfRec> g_recs;
 
@@ -41,7 +41,7 @@ Prof::Prof(int kc, cudaStream_t st, int sub, double bytes, double flops, int lau
     if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return; }
     cudaEventRecord(a, st);
     std::lock_guard<std::mutex> lk(g_mu);
-    g_recs.push_back({a, b, kc, sub, launches, bytes, flops, -1});
+    g_recs.push_back({a, b, kc, sub, launches, bytes, flops, -1, 0.0});
     rec_ = (int)g_recs.size() - 1;
 }
 
@@ -51,7 +51,7 @@ Prof::~Prof() {
     if (rec_ < (int)g_recs.size()) cudaEventRecord(g_recs[rec_].b, st_);
 }
 
-unsigned long long* Prof::area_slot() {
+unsigned long long* Prof::area_slot(double bytes_per_unit) {
     if (rec_ < 0) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_area_dev) {
@@ -61,6 +61,7 @@ unsigned long long* Prof::area_slot() {
     if (g_area_next >= AREA_SLOTS) return nullptr;
     const int slot = g_area_next++;
     g_recs[rec_].area_slot = slot;
+    g_recs[rec_].area_scale = bytes_per_unit;
     return g_area_dev + slot;
 }
 
@@ -105,7 +106,7 @@ extern "C" int rodc_profile_collect(double* fc1_ms, double* fc1_flops, int64_t* 
         RODC_CUDA(cudaEventSynchronize(r.b));
         RODC_CUDA(cudaEventElapsedTime(&t[i], r.a, r.b));
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
-        if (r.area_slot >= 0 && r.area_slot < (int)area.size()) r.bytes += 3.0 * (double)area[r.area_slot];
+        if (r.area_slot >= 0 && r.area_slot < (int)area.size()) r.bytes += r.area_scale * (double)area[r.area_slot];
         if (r.kc == KC_FC1 || r.kc == KC_FC1_SIMT) {
             ms += t[i]; fl += r.flops; ++n1;
             if (r.flops > maxfl) maxfl = r.flops;
