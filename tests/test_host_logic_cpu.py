@@ -142,3 +142,34 @@ def test_cascade_app_model_discovery_errors(tmp_path):
     with pytest.raises(FileNotFoundError):
         single._stage_files()
     pkg.cf.reset()
+
+
+def test_box_list_behaves_like_the_reference_list():
+    """`data/box_list.py`: the lazily materialised per-image result behaves like the reference's
+    ``List[LabeledBoundingBox]`` (len, iteration, indexing, ==, +, list methods) and exposes the arrays."""
+    from collections.abc import Sequence
+    from rapidobjectdetectionusingcascadedcnns_b200.data.box_list import BoxList
+    from rapidobjectdetectionusingcascadedcnns_b200.data.db import label
+    from rapidobjectdetectionusingcascadedcnns_b200.data.rectangles import LabeledBoundingBox
+    fg = label.get_by_iid(label.IID_FOREGROUND)
+    boxes = np.asarray([[1, 2, 13, 14], [5, 6, 29, 30], [7, 8, 55, 56]], np.int32)
+    img = object()
+    post = BoxList(boxes, np.asarray([3.0, 2.0, 5.0]), img, fg, post_nms=True)
+    assert isinstance(post, Sequence) and len(post) == 3 and bool(post) and post._list is None      # nothing built yet
+    np.testing.assert_array_equal(post.rows(), [[1, 2, 13, 14, 3.0], [5, 6, 29, 30, 2.0], [7, 8, 55, 56, 5.0]])
+    assert post._list is None                                       # rows() needs no object either
+    b = post[1]
+    assert isinstance(b, LabeledBoundingBox) and (b.xmin, b.ymin, b.xmax, b.ymax, b.width, b.height) == (5, 6, 29, 30, 24, 24)
+    assert isinstance(b.xmin, np.integer) and isinstance(b.confidence, float) and b.confidence == 2.0   # `app/inference_app.py:203-212`
+    assert b.image is img and b.label.is_foreground
+    assert [x.xmax for x in post] == [13, 29, 55] and post[-1].confidence == 5.0 and len(post[0:2]) == 2
+    assert list(post) == post._list and post == list(post) and not (post != list(post))
+    assert (post + [7])[-1] == 7 and ([7] + post)[0] == 7
+    post.sort(key=lambda x: x.confidence)                           # any other list method acts on the materialised list
+    assert [x.confidence for x in post] == [2.0, 3.0, 5.0]
+    post.append("x")
+    assert len(post) == 4 and post.rows.__self__ is post
+    pre = BoxList(boxes, np.asarray([0.75, 0.5, 1.0], np.float32), [img, None, img], fg, post_nms=False)
+    first = pre[0]
+    assert type(first.xmin) is int and isinstance(first.confidence, np.float32) and pre[1].image is None   # cascade `:319-334`
+    assert BoxList(boxes[:0], np.zeros((0,)), img, fg, True) == [] and not BoxList(boxes[:0], np.zeros((0,)), img, fg, True)
